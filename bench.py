@@ -1,0 +1,390 @@
+"""bench.py -- headline benchmark of the general_cf training hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload simgcl-amazon]
+
+One "step" = one iteration of trainer/trainer.py:63-68 (zero_grad, cal_loss, backward, Adam step) at
+B = 4096 on BASELINE.json configs[1]: SimGCL, d = 64, L = 3, tau = 0.2, on a synthetic graph with the
+reference's amazon shape (|U| = 76 469, |I| = 83 761, nnz = 2 x 966 680; sslrec_b200/datagen.py).
+Prints ONE JSON line (contract in the task statement):
+  value      steps/s with the batch indices already resident in HBM (CUDA events, max over ranks)
+  e2e        steps/s through the plugin surface from pinned HOST index buffers, with the H2D copy of
+             the batch and the D2H reads of loss / loss terms (loss.item(), float(v)) in the timed region
+  roofline   the propagation SpMM kernel (HBM-bound): algorithmic bytes / live CUDA-event time
+  cpu_baseline  the oracle port of the reference's CPU path, timed on this box's host cores
+``--impl reference`` times that CPU path alone (rank 0 only under torchrun).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+WORKLOADS = {
+    # name: (model, graph, model hyper-parameters)   -- BASELINE.json configs
+    'simgcl-amazon': ('simgcl', 'amazon', dict(layer_num=3, embedding_size=64, temperature=0.2, eps=0.9, cl_weight=1.0e-2,
+                                               reg_weight=1.0e-6, keep_rate=1.0)),
+    'lightgcn-gowalla': ('lightgcn', 'gowalla', dict(layer_num=3, embedding_size=64, reg_weight=1.0e-8, keep_rate=0.5)),
+    'sgl-yelp': ('sgl', 'yelp', dict(layer_num=3, embedding_size=64, temperature=0.2, cl_weight=1.0, reg_weight=1.0e-5,
+                                     keep_rate=0.5, augmentation='edge_drop')),
+}
+BATCH = 4096
+
+
+def rank_world():
+    return int(os.environ.get('RANK', 0)), int(os.environ.get('LOCAL_RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
+
+
+def graph_arrays(name):
+    from sslrec_b200.datagen import named_graph
+    cache = os.path.join('/tmp', f'sslrec_b200_graph_{name}.npz')
+    if os.path.exists(cache):
+        z = np.load(cache)
+        return z['rows'], z['cols'], int(z['n_user']), int(z['n_item'])
+    rows, cols, n_user, n_item = named_graph(name, seed=2023)
+    try:
+        np.savez(cache + f'.{os.getpid()}.npz', rows=rows, cols=cols, n_user=n_user, n_item=n_item)
+        os.replace(cache + f'.{os.getpid()}.npz', cache)
+    except OSError:
+        pass
+    return rows, cols, n_user, n_item
+
+
+def make_batches(rows, cols, n_item, count, seed=2023):
+    """``count`` batches of (ancs, poss, negs): B uniform training edges + uniform negatives (the
+    DataLoader's shuffle + sample_negs draw, pre-materialised so the timed region holds no Python sampling)."""
+    rs = np.random.RandomState(seed)
+    out = []
+    for _ in range(count):
+        pick = rs.randint(0, len(rows), size=BATCH)
+        out.append(np.stack([rows[pick], cols[pick], rs.randint(0, n_item, size=BATCH)]).astype(np.int64))
+    return out
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.gpu, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '100',
+                                          '-i', str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line)
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(',')]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[4:8]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        return json.load(open(p)), 'measured'
+    return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0}, 'fallback'
+
+
+# --------------------------------------------------------------------------------------------------
+# the CPU arm: oracle port of the reference path (oracle/cf_oracle.CpuTrainer)
+# --------------------------------------------------------------------------------------------------
+
+def cpu_steps(model, hp, rows, cols, n_user, n_item, batches, budget_s, max_steps, warmup=1):
+    from oracle import cf_oracle as O
+    adj = O.normalized_adjacency(rows, cols, n_user, n_item)
+    adj.reference_layout = True                      # the reference's column-sorted COO (data_handler_general_cf.py:69-72)
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    tr = O.CpuTrainer(model, adj, hp['embedding_size'], dict(hp, lr=1e-3))
+    tb = [tuple(torch.from_numpy(b[i]) for i in range(3)) for b in batches]
+    t_start = time.perf_counter()
+    for i in range(warmup):
+        tr.step(tb[i % len(tb)])
+    times = []
+    for i in range(max_steps):
+        t0 = time.perf_counter()
+        tr.step(tb[(warmup + i) % len(tb)])
+        times.append(time.perf_counter() - t0)
+        if time.perf_counter() - t_start > budget_s:
+            break
+    return times, threads
+
+
+def run_reference(args):
+    rank, _, world = rank_world()
+    if rank != 0:
+        return
+    model, graph, hp = WORKLOADS[args.workload]
+    rows, cols, n_user, n_item = graph_arrays(graph)
+    batches = make_batches(rows, cols, n_item, max(2, min(args.steps + args.warmup, 8)))
+    times, threads = cpu_steps(model, hp, rows, cols, n_user, n_item, batches, budget_s=170.0, max_steps=args.steps,
+                               warmup=min(args.warmup, 1))
+    ms = 1e3 * float(np.median(times))
+    val = 1e3 / ms
+    sample = (f'{len(times)} of {args.steps} full training steps executed inside the 170 s budget (median step time); '
+              f'oracle port of the reference CPU path (torch {torch.__version__} sparse COO spmm + dense InfoNCE), {threads} threads')
+    print(json.dumps({
+        'impl': 'reference', 'metric': 'train_steps_per_sec', 'value': val, 'unit': 'steps/s', 'n_gpus': args.gpus, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32',
+        'data': 'synthetic', 'config': workload_config(args.workload, n_user, n_item, len(rows), world),
+        'cpu_baseline': {'value': val, 'unit': 'steps/s', 'cores': threads, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': val, 'unit': 'steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }))
+
+
+def workload_config(name, n_user, n_item, n_edge, world):
+    model, graph, hp = WORKLOADS[name]
+    return {'workload': f'{model} training step on synthetic {graph}-shaped graph', 'model_name': model, 'graph': graph,
+            'n_user': n_user, 'n_item': n_item, 'nnz': 2 * n_edge, 'batch': BATCH, 'dim': hp['embedding_size'],
+            'layers': hp['layer_num'], 'temperature': hp.get('temperature'), 'parallelism': f'row-shard x{world}' if world > 1 else 'single GPU',
+            'l2': 'no explicit flush: each step touches > 1 GB (3-view activations, gradient sinks, split partials) >> 126 MB L2'}
+
+
+# --------------------------------------------------------------------------------------------------
+# the GPU arm
+# --------------------------------------------------------------------------------------------------
+
+def run_ours(args):
+    rank, local_rank, world = rank_world()
+    import scipy.sparse as sp
+    import sslrec_b200
+    from sslrec_b200 import _lib, engine
+    from sslrec_b200.config import default_config, load_config
+    from sslrec_b200.data_handler import DataHandlerGeneralCF
+    from sslrec_b200.optim import FusedAdam
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=dev)
+    model_name, graph, hp = WORKLOADS[args.workload]
+    rows, cols, n_user, n_item = graph_arrays(graph)
+    cfg = default_config(model_name, **hp)
+    cfg['train']['batch_size'] = BATCH
+    load_config(base=cfg, device=str(dev))
+    trn = sp.coo_matrix((np.ones(len(rows), dtype=np.float32), (rows, cols)), shape=(n_user, n_item))
+    dh = DataHandlerGeneralCF(trn)
+    dh.load_data()
+    import importlib
+    mod = importlib.import_module('sslrec_b200.general_cf.' + model_name)
+    cls = [getattr(mod, a) for a in dir(mod) if a.lower() == model_name][0]
+    torch.manual_seed(2023)
+    model = cls(dh)
+    if world > 1:
+        from sslrec_b200.parallel import RowShard
+        model.comm = RowShard(dist, rank, world, n_user + n_item)
+    model = model.to(dev)
+    opt = FusedAdam(model.parameters(), lr=1e-3, weight_decay=0)
+    K, W = args.steps, args.warmup
+    host_batches = [torch.from_numpy(b).pin_memory() for b in make_batches(rows, cols, n_item, K + W)]
+    dev_batches = [b.to(dev) for b in host_batches]
+
+    def step_resident(i):
+        opt.zero_grad()
+        b = dev_batches[i]
+        loss, parts = model.cal_loss([b[0], b[1], b[2]])
+        loss.backward()
+        opt.step()
+        return loss
+
+    def step_e2e(i):
+        opt.zero_grad()
+        b = host_batches[i].to(dev, non_blocking=True)           # trainer.py:64
+        loss, parts = model.cal_loss([b[0], b[1], b[2]])
+        v = loss.item()                                          # trainer.py:66 (D2H sync)
+        loss.backward()
+        opt.step()
+        for name in parts:                                       # trainer.py:72
+            float(parts[name])
+        return v
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn):
+        for i in range(W):
+            fn(i)
+        barrier()
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        l0 = _lib.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(K):
+            fn(W + i)
+        e1.record()
+        barrier()
+        launches = _lib.launch_count() - l0
+        clocks = sampler.stop() if rank == 0 else None
+        ms = e0.elapsed_time(e1)
+        if dist is not None:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms / K, launches, clocks
+
+    ms_res, launches, clocks = timed(step_resident)
+    ms_e2e, _, clocks_e2e = timed(step_e2e)
+
+    # ---- live kernel timings (CUDA events on the launching stream) over K more steps ----
+    engine.TIMER = engine.KernelTimer()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        step_resident(W + i)
+    e1.record()
+    barrier()
+    prof_ms = e0.elapsed_time(e1) / K
+    summ = engine.TIMER.summary()
+    engine.TIMER = None
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    peaks, peak_kind = measured_peaks()
+    N, nnz, d = n_user + n_item, 2 * len(rows), hp['embedding_size']
+    L = hp['layer_num']
+    # algorithmic bytes of one propagation launch: every stored entry moves V d-wide rows
+    # (4 V d bytes) + its (col, val) pair (8 bytes); every output row is written once per view
+    # (4 V d bytes) + its work item (16 bytes)
+    def prop_bytes(views, in_views):
+        gather_views = views if in_views == views else 1
+        return nnz * (4 * d * gather_views + 8) + N * (4 * d * views + 16)
+    prop_ms = prop_bytes_total = 0.0
+    prop_launches = 0
+    for name in ('prop_fwd', 'prop_bwd'):
+        if name in summ:
+            prop_ms += summ[name]['ms']
+            prop_launches += summ[name]['launches']
+    # per-launch bytes: recompute from the recorded metas
+    engine_records = summ
+    views = 3 if model_name in ('simgcl', 'sgl') else 1
+    launches_per_step = prop_launches / K if K else 0
+    # forward layer 1 reads the shared [N, d] input; all other launches gather `views` rows per entry
+    bytes_per_step = 0.0
+    fwd_l, bwd_l = summ.get('prop_fwd', {'launches': 0})['launches'] / K, summ.get('prop_bwd', {'launches': 0})['launches'] / K
+    if fwd_l:
+        shared_first = model_name == 'simgcl'      # SGL / LightGCN(keep<1) mask per view -> no shared layer
+        bytes_per_step += prop_bytes(views, 1 if shared_first else 1) * 1 + prop_bytes(views, views) * (fwd_l - 1)
+        if not shared_first and views > 1:
+            bytes_per_step += nnz * 4 * d * (views - 1)   # masked layer 1 still fetches the shared row once per view
+    bytes_per_step += prop_bytes(views, views) * bwd_l
+    avg_prop_ms = prop_ms / prop_launches if prop_launches else float('nan')
+    avg_bytes = bytes_per_step / launches_per_step if launches_per_step else float('nan')
+    achieved = avg_bytes / (avg_prop_ms * 1e-3) / 1e9 if prop_launches else None
+    roofline = {'kernel': 'prop_kernel (ssl_propagate_layer, fwd+bwd launches)', 'bound': 'hbm', 'achieved': achieved,
+                'peak': peaks['hbm_gbs'], 'peak_kind': peak_kind + ' (burst copy)', 'unit': 'GB/s',
+                'frac': (achieved / peaks['hbm_gbs']) if achieved else None, 'traffic': None,
+                'avg_launch_ms': avg_prop_ms, 'alg_bytes_per_launch': avg_bytes, 'launches_per_step': launches_per_step,
+                'share_of_step': prop_ms / K / prof_ms if prof_ms else None,
+                'note': 'tables (41 MB/view) are L2-resident on this graph: achieved counts L2 hits, see DESIGN.md'}
+    # the dense InfoNCE contraction, reported separately against the FP32 FMA pipe (not HBM-bound)
+    nce_ms = sum(summ[k]['ms'] for k in ('nce_gemm_fwd', 'nce_gemm_bwd') if k in summ)
+    nce_flops = 0.0
+    for k in ('nce_gemm_fwd', 'nce_gemm_bwd'):
+        if k in summ:
+            pass
+    terms = {'simgcl': [n_user, n_item], 'sgl': [n_user, n_item, n_item]}.get(model_name, [])
+    nce_flops_step = sum(8.0 * BATCH * n * d for n in terms)          # fwd 4 B N d + bwd 4 B N d per term
+    sm_mhz = (clocks or {}).get('sm_mhz') or 1965.0
+    fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
+    roofline_nce = None
+    if nce_ms:
+        tf = nce_flops_step * K / (nce_ms * 1e-3) / 1e12
+        roofline_nce = {'kernel': 'softmax_gemm_kernel (ssl_softmax_gemm, fwd+bwd)', 'bound': 'fp32_fma', 'achieved': tf,
+                        'peak': fp32_peak, 'peak_kind': f'148 SM x 128 FMA/clk x 2 x {sm_mhz:.0f} MHz (median SM clock under load)',
+                        'unit': 'TFLOP/s', 'frac': tf / fp32_peak, 'flop_per_step': nce_flops_step,
+                        'share_of_step': nce_ms / K / prof_ms}
+    emb_per_step = 2.0 * views * L * nnz if model_name != 'sgl' else 2.0 * L * nnz * (1 + 2 * hp['keep_rate'])
+
+    # ---- CPU baseline on this box's host cores (bounded sample) ----
+    cpu = None
+    if not args.no_cpu_baseline:
+        times, threads = cpu_steps(model_name, hp, rows, cols, n_user, n_item, [b.numpy() for b in host_batches[:3]],
+                                   budget_s=45.0, max_steps=2, warmup=1)
+        cpu = {'value': 1.0 / float(np.median(times)), 'unit': 'steps/s', 'cores': threads, 'kind': 'port',
+               'sample': f'{len(times)} full training steps after 1 warm-up (same graph, batch, hyper-parameters); oracle port of the reference CPU path'}
+
+    value = 1e3 / ms_res * 1.0
+    out = {
+        'metric': 'train_steps_per_sec', 'value': value, 'unit': 'steps/s', 'n_gpus': world, 'steps': K, 'warmup': W,
+        'ms_per_step': ms_res, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': workload_config(args.workload, n_user, n_item, len(rows), world),
+        'e2e': {'value': 1e3 / ms_e2e, 'unit': 'steps/s', 'ms_per_step': ms_e2e, 'h2d_bytes_per_step': 3 * BATCH * 8,
+                'd2h_bytes_per_step': 4 * (1 + len({'simgcl': 3, 'sgl': 3, 'lightgcn': 2}.get(model_name, 3) * [0]))},
+        'gpu_launches': launches, 'gpu_launches_per_step': launches / K,
+        'embeddings_propagated_per_sec': emb_per_step * value,
+        'roofline': roofline, 'roofline_infonce': roofline_nce, 'cpu_baseline': cpu,
+        'clocks': clocks, 'kernel_ms_per_step': {k: v['ms'] / K for k, v in summ.items()}, 'profiled_ms_per_step': prof_ms,
+    }
+    print(json.dumps(out))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='simgcl-amazon', choices=sorted(WORKLOADS))
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        if not torch.cuda.is_available():
+            raise SystemExit('bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)')
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

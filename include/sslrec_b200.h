@@ -1,0 +1,228 @@
+/*
+ * sslrec_b200 -- C ABI of the B200 (sm_100a) general_cf training hot path.
+ *
+ * The reference (HKUDS/SSLRec) has no FFI: its "operator interface" for this path is the set of
+ * PyTorch calls made by models/general_cf/*.py, models/loss_utils.py, models/aug_utils.py and
+ * trainer/trainer.py.  Each entry point below names the reference call site(s) it replaces
+ * (file:line, relative to the reference checkout).  INTEGRATION.md shows the ctypes binding a
+ * maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - plain C: raw device pointers, sizes, a cudaStream_t passed as void*; no torch types.
+ *   - every function returns 0 on success, a negative SSL_E_* code otherwise; the message is
+ *     available from ssl_last_error() (thread-local).  No C++ exception crosses the boundary.
+ *   - the caller owns every buffer it passes; the library owns only what lives inside an
+ *     ssl_plan (work lists + split-row scratch).  Kernels are enqueued on the given stream and
+ *     never synchronise it (ssl_plan_create synchronises once, for its uploads).
+ *   - all floating point is fp32; node / item ids inside batches are int64 (trainer.py:64),
+ *     CSR indices are int32.
+ *   - "table view": a [rows, dim] fp32 matrix addressed as base + row * stride (stride in
+ *     floats), so one view of the interleaved [N, V, dim] propagation output is
+ *     (E + v*dim, V*dim) without a copy.
+ */
+#ifndef SSLREC_B200_H
+#define SSLREC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define SSL_API __attribute__((visibility("default")))
+#else
+#define SSL_API
+#endif
+
+#define SSL_OK 0
+#define SSL_E_ARG (-1)     /* bad argument (shape, null pointer, unsupported dim) */
+#define SSL_E_CUDA (-2)    /* a CUDA runtime call or kernel launch failed */
+#define SSL_E_ALLOC (-3)
+
+#define SSL_MAX_VIEWS 4
+#define SSL_MAX_SUM_SRC 6
+#define SSL_MAX_DIM 128    /* embedding_size must be a multiple of 4 and <= 128 */
+
+SSL_API int ssl_version(void);
+SSL_API const char *ssl_last_error(void);
+/* number of kernel launches issued by this library since load (bench.py's gpu_launches) */
+SSL_API int64_t ssl_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * a1/a2  adjacency plan -- replaces the torch sparse COO tensor built by
+ * data_utils/data_handler_general_cf.py:53-73 as the operand of t.spmm (lightgcn.py:28-29).
+ * CSR of the (row block of the) normalised adjacency; the structure and values are symmetric,
+ * so the same plan serves A and A^T.
+ *   h_rowptr  host  int32 [n_rows+1]   (read during create only)
+ *   d_colidx  device int32 [nnz]       global column (node) ids, ascending inside a row
+ *   d_vals    device fp32  [nnz]
+ *   d_rev     device int32 [nnz] or NULL: position of the reverse entry (col,row); only needed
+ *             when an *injected* edge mask is used together with transpose = 1
+ *   row_offset  global id of local row 0 (row-sharded multi-GPU; 0 on one GPU)
+ * ------------------------------------------------------------------------------------------ */
+typedef struct ssl_plan ssl_plan;
+
+SSL_API int ssl_plan_create(ssl_plan **out, const int32_t *h_rowptr, const int32_t *d_colidx, const float *d_vals,
+                    const int32_t *d_rev, int64_t n_rows, int64_t n_cols, int64_t nnz, int64_t row_offset,
+                    void *stream);
+SSL_API int ssl_plan_destroy(ssl_plan *plan);
+/* work-list statistics: out[0]=items, out[1]=split rows, out[2]=segments, out[3]=max row nnz */
+SSL_API int ssl_plan_stats(const ssl_plan *plan, int64_t out[4]);
+
+/* ------------------------------------------------------------------------------------------
+ * a2-a10  one propagation layer for up to SSL_MAX_VIEWS augmented views at once.
+ *
+ *   acc_v[r]  = sum_p  m_v(p) * s_v * val[p] * x_in[col[p], v]          (CSR row r)
+ *   x_v[r]    = acc_v[r] + residual[r, v]                                 (residual optional)
+ *   x_v[r]   += eps * sign(x_v[r]) * u / max(|u|_2, 1e-12)                (noise_mode != 0)
+ *   x_out[r, v]   = x_v[r]                                                (x_out optional)
+ *   sum_out[r, v] = x_v[r] + sum_i sum_src[i][r, v]                       (sum_out optional;
+ *                   reduce_views: sum_out[r] = sum_v of the above, + reg_coef * reg_src[r])
+ *
+ * replaces: t.spmm (lightgcn.py:29, hccf.py:36), the layer sum (lightgcn.py:41, simgcl.py:29,
+ * sgl.py:34, ncl.py:41), EdgeDrop (aug_utils.py:18-31) as an in-kernel keep test so no second
+ * adjacency is built, EmbedPerturb (aug_utils.py:125-132) as an epilogue, and -- with
+ * transpose = 1 and residual = upstream gradient -- the autograd backward of all of them
+ * (dX = A_v^T dY evaluated on the same CSR with the mask key swapped).
+ *
+ * Layouts: x_in [n_cols, in_views, dim] (in_views = 1: all views read the same rows, or
+ * = n_views); x_out, residual [n_rows, n_views, dim]; sum_src[i] [n_rows, sum_src_views[i], dim]
+ * with sum_src_views[i] in {1, n_views}; sum_out [n_rows, n_views, dim] or [n_rows, dim].
+ * Row-wise pointers are indexed by LOCAL row (0..n_rows), x_in by global column id.
+ *
+ * edge_mode[v]: 0 keep all; 1 counter-based RNG: keep iff U(seed[v], edge_stream_id, row, col) >= 1-keep
+ *               (floor(U + keep), aug_utils.py:28); 2 injected: edge_mask[v][p] != 0, p = CSR
+ *               position (rev[p] when transpose).  edge_scale[v] multiplies kept values
+ *               (1, or 1/keep for EdgeDrop(resize_val=True), hccf.py:33).
+ * noise_mode[v]: 0 none; 1 RNG uniform(seed[v], noise_stream_id, row, elem);
+ *               2 injected: noise_u[v] is a [n_rows, dim] U[0,1) tensor.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct ssl_prop_args {
+    int32_t dim, n_views, in_views, transpose;
+    const float *x_in;
+    float *x_out;
+    float *sum_out;
+    const float *residual;
+    int32_t reduce_views;
+    int32_t n_sum_src;
+    const float *sum_src[SSL_MAX_SUM_SRC];
+    int32_t sum_src_views[SSL_MAX_SUM_SRC];
+    float reg_coef;
+    const float *reg_src;             /* [n_rows, dim]; only with reduce_views */
+    int32_t edge_mode[SSL_MAX_VIEWS];
+    float edge_keep[SSL_MAX_VIEWS];
+    float edge_scale[SSL_MAX_VIEWS];
+    const uint8_t *edge_mask[SSL_MAX_VIEWS];
+    int32_t noise_mode[SSL_MAX_VIEWS];
+    const float *noise_u[SSL_MAX_VIEWS];
+    float noise_eps;
+    uint64_t seed[SSL_MAX_VIEWS];
+    uint32_t edge_stream_id;          /* RNG sub-stream of the edge mask: constant over the layers of one forward
+                                         (lightgcn.py:36-37, sgl.py:27-28) or the layer index (hccf.py:47) */
+    uint32_t noise_stream_id;         /* RNG sub-stream of the perturbation: the layer index (simgcl.py:26-27) */
+} ssl_prop_args;
+
+SSL_API int ssl_propagate_layer(const ssl_plan *plan, const ssl_prop_args *args, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a9  NodeDrop (aug_utils.py:40-50, sgl.py:24-25).
+ * forward : out[r, v] = x[r] * m_v(r)            x [n, dim] -> out [n, n_views, dim]
+ * backward: out[r]   += sum_v g[r, v] * m_v(r)   g [n, n_views, dim] -> out [n, dim]  (accumulate)
+ * mode[v]: 0 keep all; 1 RNG keep iff U(seed[v], row) >= 1-keep; 2 injected mask[v][r] != 0.
+ * ------------------------------------------------------------------------------------------ */
+SSL_API int ssl_node_drop(const float *x, float *out, int64_t n, int32_t dim, int32_t n_views, int32_t backward,
+                  const int32_t *mode, const float *keep, const uint8_t *const *mask, const uint64_t *seed,
+                  int64_t row_offset, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a11+a12  gathers + BPR  (lightgcn.py:48-52, loss_utils.py:7-10; hccf.py:70-74 is the same
+ * function written as -log sigmoid).  loss_b = softplus(a.n - a.p), coef_b = sigmoid(a.n - a.p).
+ * users / items are table views; ancs index the user view, poss/negs the item view.
+ * ssl_bpr_bwd adds scale * (*gscale) * d loss_b into the gradient views (atomicAdd: batch
+ * indices repeat; the reference's index_put_(accumulate) does the same).
+ * ------------------------------------------------------------------------------------------ */
+SSL_API int ssl_bpr_fwd(const float *users, int64_t u_stride, const float *items, int64_t i_stride,
+                const int64_t *ancs, const int64_t *poss, const int64_t *negs, int64_t batch, int32_t dim,
+                float *loss_b, float *coef_b, void *stream);
+SSL_API int ssl_bpr_bwd(const float *users, int64_t u_stride, const float *items, int64_t i_stride,
+                const int64_t *ancs, const int64_t *poss, const int64_t *negs, int64_t batch, int32_t dim,
+                const float *coef_b, const float *gscale, float scale,
+                float *g_users, int64_t gu_stride, float *g_items, int64_t gi_stride, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a13/a14  InfoNCE, never materialising the [B, N_side] logits
+ * (loss_utils.py:30-39 cal_infonce_loss; :42-51 cal_infonce_loss_spec_nodes with norm_mode 1).
+ *
+ * ssl_rows_normalize  x^ = x / sqrt(1e-8 + |x|^2)  (norm_mode 0, loss_utils.py:33-35) or
+ *                     F.normalize(x + 1e-8)        (norm_mode 1, loss_utils.py:45-46);
+ *   optional gather (idx != NULL: row i of the output is x[idx[i]]), optional scale of the
+ *   output (alpha), writes row-major out [n, dim], the K-major tile copy out_t
+ *   [ceil(n/64), dim, 64] the streaming side of ssl_softmax_gemm reads (may be NULL), and
+ *   rinv [n] (the 1/norm used, needed by the backward).
+ * ssl_softmax_gemm    for every row r of R [n_r, dim] over the rows c of C (row-major C
+ *   [n_c, dim] and its K-major tile copy C_t):   e = exp2(R_r . C_c - offset) * colscale[c]
+ *   rowsum_part[s, r] = sum_c e   (optional)     o_part[s, r, :] = sum_c e * C_c
+ *   for the s-th of n_split contiguous chunks of C.  One launch does the forward of a term
+ *   (R = scaled anchors, C = normalised table: log-sum-exp and the softmax-weighted table
+ *   average that is the anchor gradient) and, with the roles swapped, its backward
+ *   (R = table tile, C = anchors, colscale = g/rowsum: the dense table gradient).
+ * ------------------------------------------------------------------------------------------ */
+SSL_API int ssl_rows_normalize(const float *x, int64_t stride, const int64_t *idx, int64_t n, int32_t dim, int32_t norm_mode,
+                       float alpha, float *out, float *out_t, float *rinv, void *stream);
+SSL_API int ssl_softmax_gemm(const float *R, int64_t n_r, const float *C, const float *C_t, int64_t n_c, int32_t dim,
+                     const float *colscale, float offset, int32_t n_split, float *rowsum_part, float *o_part,
+                     void *stream);
+/* forward epilogue of one term: reduces the split partials and produces, per anchor b,
+ *   rowsum[b] (+ deno_eps), obar[b,:] = o[b,:]/rowsum[b] and
+ *   loss_b[b] = -(a^_b . p^_b)/tau + 1/tau + ln(rowsum[b])          */
+SSL_API int ssl_nce_finalize(const float *rowsum_part, const float *o_part, int32_t n_split, int64_t batch, int32_t dim,
+                     const float *a_hat, const float *p_hat, float tau, float deno_eps,
+                     float *rowsum, float *obar, float *loss_b, void *stream);
+/* backward w.r.t. the gathered rows: d a^ = g/tau (obar - p^), d p^ = -g/tau a^, pushed through
+ * the normalisation (de = rinv (dx^ - x^ (x^ . dx^))) and atomically added to the gradient views.
+ * g = scale * (*gscale).  g1 / g2 may be NULL (NCL prototypes, HCCF's detached side). */
+SSL_API int ssl_nce_bwd_rows(const float *a_hat, const float *p_hat, const float *obar, const float *rinv1, const float *rinv2,
+                     const int64_t *idx, int64_t batch, int32_t dim, float tau, const float *gscale, float scale,
+                     float *g1, int64_t g1_stride, float *g2, int64_t g2_stride, void *stream);
+/* backward w.r.t. the table: dt^ = sum of the split partials of the swapped ssl_softmax_gemm;
+ * g_table[j] (+)= rinv_j (dt^_j - t^_j (t^_j . dt^_j)) */
+SSL_API int ssl_nce_bwd_table(const float *dt_part, int32_t n_split, const float *t_hat, const float *rinv, int64_t n,
+                      int32_t dim, float *g_table, int64_t g_stride, int32_t accumulate, void *stream);
+/* colscale[b] = scale * (*gscale) * ln2 / rowsum[b] for the swapped gemm */
+SSL_API int ssl_nce_colscale(const float *rowsum, int64_t batch, const float *gscale, float scale, float *colscale, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a15  reg_params (loss_utils.py:20-24): out[0] = sum x^2, deterministic two-stage reduction.
+ * ssl_sum: out[0] = alpha * sum x (same reduction; used for the per-sample loss vectors).
+ * ssl_axpy: y += alpha * (*gscale) * x  (gradient of the regulariser, 2 * reg_weight * W).
+ * ------------------------------------------------------------------------------------------ */
+SSL_API int ssl_sumsq(const float *x, int64_t n, float *out, void *stream);
+SSL_API int ssl_sum(const float *x, int64_t n, float alpha, float *out, void *stream);
+SSL_API int ssl_axpy(const float *x, float *y, int64_t n, const float *gscale, float alpha, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a20  Adam (trainer.py:45-49,68 -> torch.optim.Adam, amsgrad off): one fused pass over
+ * p, g, m, v.  step is 1-based; weight_decay is folded into g as torch does.
+ * ------------------------------------------------------------------------------------------ */
+SSL_API int ssl_adam_step(float *p, const float *g, float *m, float *v, int64_t n, int64_t step, float lr, float beta1,
+                  float beta2, float eps, float weight_decay, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a18  full_predict + _mask_predict (lightgcn.py:58-66, base_model.py:35-36) and the top-k that
+ * consumes it (metrics.py:108).
+ * ssl_predict_mask: preds[b, i] = (U[users[b]] . I[i]) * (1 - M[b,i]) - 1e8 * M[b,i]; the mask is
+ *   either the dense int64 [n_b, n_item] tensor the reference passes (mask_dense) or, when that
+ *   is NULL, the training CSR (trn_rowptr int32 [n_user+1], trn_cols int32) read on device.
+ * ssl_topk: the k largest entries of every row, descending, ties broken by the lower index.
+ * ------------------------------------------------------------------------------------------ */
+SSL_API int ssl_predict_mask(const float *users_tab, int64_t u_stride, const float *items_tab, int64_t i_stride,
+                     const int64_t *users, int64_t n_b, int64_t n_item, int32_t dim, const int64_t *mask_dense,
+                     const int32_t *trn_rowptr, const int32_t *trn_cols, float *preds, void *stream);
+SSL_API int ssl_topk(const float *preds, int64_t n_b, int64_t n_item, int32_t k, int64_t *out_idx, float *out_val, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SSLREC_B200_H */

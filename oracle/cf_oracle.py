@@ -55,6 +55,8 @@ class Adj:
     def nnz(self) -> int:
         return int(self.rows.shape[0])
 
+    reference_layout: bool = False   # emit COO entries in the reference's (column-sorted) order
+
     def torch_coo(self, dtype=torch.float32, vals: Optional[torch.Tensor] = None,
                   keep: Optional[np.ndarray] = None) -> torch.Tensor:
         r, c = self.rows, self.cols
@@ -62,6 +64,9 @@ class Adj:
         if keep is not None:
             k = torch.from_numpy(np.asarray(keep, dtype=bool))
             r, c, v = r[keep], c[keep], v[k]
+        if self.reference_layout:
+            o = np.lexsort((r, c))
+            r, c, v = r[o], c[o], v[torch.from_numpy(o)]
         idx = torch.from_numpy(np.vstack([r, c]).astype(np.int64))
         return torch.sparse_coo_tensor(idx, v, (self.n, self.n), check_invariants=False)
 

@@ -1,0 +1,401 @@
+// Multi-view CSR SpMM propagation layer with in-kernel augmentation (include/sslrec_b200.h,
+// ssl_propagate_layer).  HBM/L2-bound gather: no tensor cores (there is no dense contraction).
+//
+// Mapping.  A "group" of G = pow2(dim/4) lanes owns one work item (a CSR row, or a <= seg_len
+// slice of a long row); each lane owns one float4 column slot of every view, so a neighbour row
+// of view v is fetched by one coalesced 16 B x G request (256 B for dim = 64).  32/G items per
+// warp.  The group's lanes first load G (col, val) pairs coalesced, evaluate the edge keep test
+// once per edge (not once per lane), then broadcast them with shuffles while the row gathers are
+// issued four edges deep.  Items are sorted by length (split segments first, then rows by
+// descending degree) so the groups of a warp run equal trip counts and the heavy items start
+// first.  Long rows are split into segments whose partial sums go to a plan-owned scratch; the
+// last segment to finish (atomic ticket) adds the partials in segment order -- the summation
+// order of every output element is fixed, so results are bit-reproducible run to run.
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+#include "common.cuh"
+
+struct ssl_plan {
+    int64_t n_rows, n_cols, nnz, row_offset;
+    const int32_t *colidx;
+    const float *vals;
+    const int32_t *rev;
+    int4 *items;        // {local row, edge begin, edge end, long-row id or -1}
+    int2 *long_info;    // per long row: {first slot, n segments}
+    int32_t *counters;  // per long row: arrival ticket
+    float *partial;     // [n_slots, SSL_MAX_VIEWS * SSL_MAX_DIM]
+    int64_t n_items, n_long, n_slots, max_deg;
+};
+
+namespace {
+
+constexpr int kMinSeg = 128;       // rows up to this many entries are never split
+constexpr int kThreads = 256;
+constexpr int kPartialStride = SSL_MAX_VIEWS * SSL_MAX_DIM;
+
+struct PlanDev {
+    const int32_t *colidx;
+    const float *vals;
+    const int32_t *rev;
+    const int4 *items;
+    const int2 *long_info;
+    int32_t *counters;
+    float *partial;
+    int64_t n_items;
+    uint32_t row_offset;
+};
+
+__device__ __forceinline__ float sgnf(float x) { return (x > 0.f) ? 1.f : ((x < 0.f) ? -1.f : 0.f); }
+
+template <int G, int V, bool SHARED>
+__global__ void __launch_bounds__(kThreads) prop_kernel(PlanDev p, ssl_prop_args a) {
+    constexpr int RPW = 32 / G;
+    constexpr int NA = SHARED ? 1 : V;
+    const int lane = threadIdx.x & 31;
+    const int gl = lane % G;
+    const int grp = lane / G;
+    const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (grp * G));
+    const int64_t warp = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+    const int64_t item_idx = warp * RPW + grp;
+    const int dim = a.dim;
+    const int col = gl * 4;
+    const bool lane_on = col < dim;
+
+    int4 it = make_int4(-1, 0, 0, -1);
+    if (item_idx < p.n_items) it = p.items[item_idx];
+    const int r = it.x;
+    const uint32_t grow = p.row_offset + (uint32_t)r;
+
+    float4 acc[NA];
+#pragma unroll
+    for (int v = 0; v < NA; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    const size_t in_row = (size_t)a.in_views * dim;
+    for (int base = it.y; base < it.z; base += G) {
+        const int pe = base + gl;
+        const bool valid = pe < it.z;
+        const int c = valid ? __ldg(p.colidx + pe) : 0;
+        const float w = valid ? __ldg(p.vals + pe) : 0.f;
+        float wv[NA];
+#pragma unroll
+        for (int v = 0; v < NA; ++v) {
+            float f = w;
+            if (!SHARED) {
+                const int mode = a.edge_mode[v];
+                if (mode == 1) {
+                    const uint32_t kr = a.transpose ? (uint32_t)c : grow;
+                    const uint32_t kc = a.transpose ? grow : (uint32_t)c;
+                    f = (valid && ssl::edge_keep_rng(a.seed[v], a.edge_stream_id, kr, kc, a.edge_keep[v])) ? w * a.edge_scale[v] : 0.f;
+                } else if (mode == 2) {
+                    const int q = valid ? (a.transpose ? __ldg(p.rev + pe) : pe) : 0;
+                    f = (valid && a.edge_mask[v][q]) ? w * a.edge_scale[v] : 0.f;
+                }
+            }
+            wv[v] = f;
+        }
+        const int cnt = min(G, it.z - base);
+        for (int j = 0; j < cnt; j += 4) {
+            int cj[4];
+            float wj[4][NA];
+            float4 x[4][NA];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                cj[u] = __shfl_sync(gmask, c, j + u, G);
+#pragma unroll
+                for (int v = 0; v < NA; ++v) wj[u][v] = __shfl_sync(gmask, wv[v], j + u, G);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float *xr = a.x_in + (size_t)cj[u] * in_row + col;
+#pragma unroll
+                for (int v = 0; v < NA; ++v) {
+                    x[u][v] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (lane_on && wj[u][v] != 0.f) x[u][v] = ssl::ldg4(xr + ((a.in_views == 1) ? 0 : v * dim));
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int v = 0; v < NA; ++v) ssl::fma4(acc[v], wj[u][v], x[u][v]);
+        }
+    }
+    if (r < 0) return;
+
+    // ---- split rows: publish the partial, the last arrival reduces in segment order ----
+    if (it.w >= 0) {
+        const int2 li = p.long_info[it.w];
+        float *mine = p.partial + (size_t)item_idx * kPartialStride;   // split items are items [0, n_slots)
+        if (lane_on) {
+#pragma unroll
+            for (int v = 0; v < NA; ++v) *reinterpret_cast<float4 *>(mine + v * dim + col) = acc[v];
+        }
+        __threadfence();
+        int last = 0;
+        if (gl == 0) last = (atomicAdd(p.counters + it.w, 1) == li.y - 1);
+        last = __shfl_sync(gmask, last, 0, G);
+        if (!last) return;
+        __threadfence();
+#pragma unroll
+        for (int v = 0; v < NA; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int s = 0; s < li.y; ++s) {
+            const float *ps = p.partial + (size_t)(li.x + s) * kPartialStride;
+            if (lane_on) {
+#pragma unroll
+                for (int v = 0; v < NA; ++v) ssl::add4(acc[v], __ldcg(reinterpret_cast<const float4 *>(ps + v * dim + col)));
+            }
+        }
+        if (gl == 0) p.counters[it.w] = 0;   // ready for the next launch (stream ordered)
+    }
+
+    // ---- epilogue: residual, perturbation, layer output, layer sum ----
+    float4 tot = make_float4(0.f, 0.f, 0.f, 0.f);
+    const size_t out_row = (size_t)r * V * dim;
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        float4 x = acc[SHARED ? 0 : v];
+        if (a.residual != nullptr && lane_on) ssl::add4(x, ssl::ldg4(a.residual + out_row + v * dim + col));
+        const int nm = a.noise_mode[v];
+        if (nm != 0) {
+            float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (lane_on) {
+                if (nm == 1) u = ssl::noise_u4_rng(a.seed[v], a.noise_stream_id, grow, (uint32_t)gl);
+                else u = ssl::ldg4(a.noise_u[v] + (size_t)r * dim + col);
+            }
+            float ss = u.x * u.x + u.y * u.y + u.z * u.z + u.w * u.w;
+#pragma unroll
+            for (int o = G / 2; o > 0; o >>= 1) ss += __shfl_xor_sync(gmask, ss, o, G);
+            const float sc = a.noise_eps / fmaxf(sqrtf(ss), 1e-12f);   // F.normalize(p=2, eps=1e-12) * eps
+            x.x += sgnf(x.x) * (u.x * sc);
+            x.y += sgnf(x.y) * (u.y * sc);
+            x.z += sgnf(x.z) * (u.z * sc);
+            x.w += sgnf(x.w) * (u.w * sc);
+        }
+        if (!lane_on) continue;
+        if (a.x_out != nullptr) *reinterpret_cast<float4 *>(a.x_out + out_row + v * dim + col) = x;
+        if (a.sum_out != nullptr) {
+            for (int i = 0; i < a.n_sum_src; ++i) {
+                const int sv = a.sum_src_views[i];
+                ssl::add4(x, ssl::ldg4(a.sum_src[i] + ((size_t)r * sv + (sv == 1 ? 0 : v)) * dim + col));
+            }
+            if (a.reduce_views) ssl::add4(tot, x);
+            else *reinterpret_cast<float4 *>(a.sum_out + out_row + v * dim + col) = x;
+        }
+    }
+    if (a.sum_out != nullptr && a.reduce_views && lane_on) {
+        if (a.reg_src != nullptr) ssl::fma4(tot, a.reg_coef, ssl::ldg4(a.reg_src + (size_t)r * dim + col));
+        *reinterpret_cast<float4 *>(a.sum_out + (size_t)r * dim + col) = tot;
+    }
+}
+
+template <int G, int V>
+int launch_gv(const ssl_plan *plan, const ssl_prop_args &a, bool shared, cudaStream_t st) {
+    PlanDev p{plan->colidx, plan->vals, plan->rev, plan->items, plan->long_info, plan->counters,
+              plan->partial, plan->n_items, (uint32_t)plan->row_offset};
+    constexpr int RPW = 32 / G;
+    const int64_t items_per_block = (int64_t)(kThreads / 32) * RPW;
+    const int64_t grid = (plan->n_items + items_per_block - 1) / items_per_block;
+    if (grid == 0) return SSL_OK;
+    if (shared) prop_kernel<G, V, true><<<(unsigned)grid, kThreads, 0, st>>>(p, a);
+    else prop_kernel<G, V, false><<<(unsigned)grid, kThreads, 0, st>>>(p, a);
+    SSL_LAUNCH_CHECK("prop_kernel");
+    return SSL_OK;
+}
+
+template <int G>
+int launch_g(const ssl_plan *plan, const ssl_prop_args &a, bool shared, cudaStream_t st) {
+    switch (a.n_views) {
+        case 1: return launch_gv<G, 1>(plan, a, shared, st);
+        case 2: return launch_gv<G, 2>(plan, a, shared, st);
+        case 3: return launch_gv<G, 3>(plan, a, shared, st);
+        case 4: return launch_gv<G, 4>(plan, a, shared, st);
+    }
+    return SSL_E_ARG;
+}
+
+}  // namespace
+
+extern "C" int ssl_plan_create(ssl_plan **out, const int32_t *h_rowptr, const int32_t *d_colidx, const float *d_vals,
+                               const int32_t *d_rev, int64_t n_rows, int64_t n_cols, int64_t nnz, int64_t row_offset,
+                               void *stream) {
+    SSL_CHECK_ARG(out && h_rowptr, "ssl_plan_create: null argument");
+    SSL_CHECK_ARG(nnz == 0 || (d_colidx && d_vals), "ssl_plan_create: null CSR arrays");
+    SSL_CHECK_ARG(n_rows >= 0 && n_cols > 0 && nnz >= 0 && nnz < (int64_t)INT32_MAX, "ssl_plan_create: bad sizes");
+    SSL_CHECK_ARG(h_rowptr[0] == 0 && h_rowptr[n_rows] == nnz, "ssl_plan_create: rowptr does not span nnz");
+    cudaStream_t st = (cudaStream_t)stream;
+
+    // ---- host work list: split long rows, then whole rows by descending degree (counting sort) ----
+    std::vector<int4> items;
+    std::vector<int2> longs;
+    std::vector<int64_t> bucket(kMinSeg + 2, 0);
+    int64_t max_deg = 0;
+    for (int64_t r = 0; r < n_rows; ++r) {
+        const int64_t deg = (int64_t)h_rowptr[r + 1] - h_rowptr[r];
+        SSL_CHECK_ARG(deg >= 0, "ssl_plan_create: rowptr not monotone at row %lld", (long long)r);
+        max_deg = std::max(max_deg, deg);
+        if (deg > kMinSeg) {
+            // segment length ~ 2 sqrt(deg): the serial segment walk and the serial fix-up stay balanced
+            int64_t seg = (int64_t)std::ceil(2.0 * std::sqrt((double)deg));
+            seg = std::max<int64_t>(kMinSeg, (seg + kMinSeg - 1) / kMinSeg * kMinSeg);
+            const int64_t nseg = (deg + seg - 1) / seg;
+            longs.push_back(make_int2((int)items.size(), (int)nseg));
+            for (int64_t s = 0; s < nseg; ++s) {
+                const int64_t b = h_rowptr[r] + s * seg;
+                items.push_back(make_int4((int)r, (int)b, (int)std::min<int64_t>(b + seg, h_rowptr[r + 1]), (int)longs.size() - 1));
+            }
+        } else {
+            bucket[deg + 1]++;
+        }
+    }
+    const int64_t n_slots = (int64_t)items.size();
+    // descending-degree placement of the whole rows
+    std::vector<int64_t> start(kMinSeg + 2, 0);
+    {
+        int64_t pos = n_slots;
+        for (int d = kMinSeg; d >= 0; --d) {
+            start[d] = pos;
+            pos += bucket[d + 1];
+        }
+        items.resize(pos);
+    }
+    for (int64_t r = 0; r < n_rows; ++r) {
+        const int64_t deg = (int64_t)h_rowptr[r + 1] - h_rowptr[r];
+        if (deg <= kMinSeg) items[start[deg]++] = make_int4((int)r, h_rowptr[r], h_rowptr[r + 1], -1);
+    }
+
+    ssl_plan *p = new (std::nothrow) ssl_plan();
+    if (!p) {
+        ssl::set_error("ssl_plan_create: out of host memory");
+        return SSL_E_ALLOC;
+    }
+    *p = ssl_plan{};
+    p->n_rows = n_rows; p->n_cols = n_cols; p->nnz = nnz; p->row_offset = row_offset;
+    p->colidx = d_colidx; p->vals = d_vals; p->rev = d_rev;
+    p->n_items = (int64_t)items.size(); p->n_long = (int64_t)longs.size(); p->n_slots = n_slots; p->max_deg = max_deg;
+    auto fail = [&](cudaError_t e, const char *what) {
+        ssl::set_error("ssl_plan_create: %s: %s", what, cudaGetErrorString(e));
+        ssl_plan_destroy(p);
+        return SSL_E_CUDA;
+    };
+    cudaError_t e;
+    if (p->n_items) {
+        if ((e = cudaMalloc(&p->items, sizeof(int4) * p->n_items)) != cudaSuccess) return fail(e, "cudaMalloc items");
+        if ((e = cudaMemcpyAsync(p->items, items.data(), sizeof(int4) * p->n_items, cudaMemcpyHostToDevice, st)) != cudaSuccess)
+            return fail(e, "copy items");
+    }
+    if (p->n_long) {
+        if ((e = cudaMalloc(&p->long_info, sizeof(int2) * p->n_long)) != cudaSuccess) return fail(e, "cudaMalloc long_info");
+        if ((e = cudaMalloc(&p->counters, sizeof(int32_t) * p->n_long)) != cudaSuccess) return fail(e, "cudaMalloc counters");
+        if ((e = cudaMalloc(&p->partial, sizeof(float) * kPartialStride * p->n_slots)) != cudaSuccess) return fail(e, "cudaMalloc partial");
+        if ((e = cudaMemcpyAsync(p->long_info, longs.data(), sizeof(int2) * p->n_long, cudaMemcpyHostToDevice, st)) != cudaSuccess)
+            return fail(e, "copy long_info");
+        if ((e = cudaMemsetAsync(p->counters, 0, sizeof(int32_t) * p->n_long, st)) != cudaSuccess) return fail(e, "memset counters");
+    }
+    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return fail(e, "synchronize");   // host vectors die here
+    *out = p;
+    return SSL_OK;
+}
+
+extern "C" int ssl_plan_destroy(ssl_plan *p) {
+    if (!p) return SSL_OK;
+    cudaFree(p->items);
+    cudaFree(p->long_info);
+    cudaFree(p->counters);
+    cudaFree(p->partial);
+    delete p;
+    return SSL_OK;
+}
+
+extern "C" int ssl_plan_stats(const ssl_plan *p, int64_t out[4]) {
+    SSL_CHECK_ARG(p && out, "ssl_plan_stats: null argument");
+    out[0] = p->n_items; out[1] = p->n_long; out[2] = p->n_slots; out[3] = p->max_deg;
+    return SSL_OK;
+}
+
+extern "C" int ssl_propagate_layer(const ssl_plan *plan, const ssl_prop_args *args, void *stream) {
+    SSL_CHECK_ARG(plan && args, "ssl_propagate_layer: null argument");
+    const ssl_prop_args &a = *args;
+    SSL_CHECK_ARG(a.dim >= 4 && a.dim <= SSL_MAX_DIM && a.dim % 4 == 0, "ssl_propagate_layer: dim %d must be a multiple of 4 in [4, %d]", a.dim, SSL_MAX_DIM);
+    SSL_CHECK_ARG(a.n_views >= 1 && a.n_views <= SSL_MAX_VIEWS, "ssl_propagate_layer: n_views %d out of range", a.n_views);
+    SSL_CHECK_ARG(a.in_views == 1 || a.in_views == a.n_views, "ssl_propagate_layer: in_views must be 1 or n_views");
+    SSL_CHECK_ARG(a.x_in != nullptr, "ssl_propagate_layer: x_in is null");
+    SSL_CHECK_ARG(a.x_out != nullptr || a.sum_out != nullptr, "ssl_propagate_layer: no output requested");
+    SSL_CHECK_ARG(a.n_sum_src >= 0 && a.n_sum_src <= SSL_MAX_SUM_SRC, "ssl_propagate_layer: n_sum_src out of range");
+    SSL_CHECK_ARG(a.reg_src == nullptr || a.reduce_views, "ssl_propagate_layer: reg_src needs reduce_views");
+    bool any_edge = false;
+    for (int v = 0; v < a.n_views; ++v) {
+        SSL_CHECK_ARG(a.edge_mode[v] >= 0 && a.edge_mode[v] <= 2 && a.noise_mode[v] >= 0 && a.noise_mode[v] <= 2, "ssl_propagate_layer: bad mode for view %d", v);
+        SSL_CHECK_ARG(a.edge_mode[v] != 2 || a.edge_mask[v] != nullptr, "ssl_propagate_layer: injected edge mask missing for view %d", v);
+        SSL_CHECK_ARG(a.edge_mode[v] != 2 || !a.transpose || plan->rev != nullptr, "ssl_propagate_layer: injected mask with transpose needs the plan's rev array");
+        SSL_CHECK_ARG(a.noise_mode[v] != 2 || a.noise_u[v] != nullptr, "ssl_propagate_layer: injected noise missing for view %d", v);
+        any_edge |= a.edge_mode[v] != 0;
+    }
+    for (int i = 0; i < a.n_sum_src; ++i)
+        SSL_CHECK_ARG(a.sum_src[i] && (a.sum_src_views[i] == 1 || a.sum_src_views[i] == a.n_views), "ssl_propagate_layer: bad sum_src %d", i);
+    const bool shared = (a.in_views == 1) && !any_edge;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int quads = a.dim / 4;
+    if (quads <= 4) return launch_g<4>(plan, a, shared, st);
+    if (quads <= 8) return launch_g<8>(plan, a, shared, st);
+    if (quads <= 16) return launch_g<16>(plan, a, shared, st);
+    return launch_g<32>(plan, a, shared, st);
+}
+
+// ---------------------------------------------------------------------------------------------
+// NodeDrop
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct NodeArgs {
+    int32_t mode[SSL_MAX_VIEWS];
+    float keep[SSL_MAX_VIEWS];
+    const uint8_t *mask[SSL_MAX_VIEWS];
+    uint64_t seed[SSL_MAX_VIEWS];
+};
+
+__global__ void node_drop_kernel(const float *__restrict__ x, float *__restrict__ out, int64_t n, int dim, int n_views,
+                                 int backward, NodeArgs na, uint32_t row_offset) {
+    const int quads = dim / 4;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * quads) return;
+    const int64_t r = i / quads;
+    const int q = (int)(i % quads);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 xin = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!backward) xin = ssl::ldg4(x + r * dim + q * 4);
+    for (int v = 0; v < n_views; ++v) {
+        bool keep = true;
+        if (na.mode[v] == 1) keep = ssl::node_keep_rng(na.seed[v], row_offset + (uint32_t)r, na.keep[v]);
+        else if (na.mode[v] == 2) keep = na.mask[v][r] != 0;
+        if (!backward) {
+            *reinterpret_cast<float4 *>(out + ((size_t)r * n_views + v) * dim + q * 4) = keep ? xin : make_float4(0.f, 0.f, 0.f, 0.f);
+        } else if (keep) {
+            ssl::add4(acc, ssl::ldg4(x + ((size_t)r * n_views + v) * dim + q * 4));
+        }
+    }
+    if (backward) {
+        float4 *o = reinterpret_cast<float4 *>(out + r * dim + q * 4);
+        float4 cur = *o;
+        ssl::add4(cur, acc);
+        *o = cur;
+    }
+}
+}  // namespace
+
+extern "C" int ssl_node_drop(const float *x, float *out, int64_t n, int32_t dim, int32_t n_views, int32_t backward,
+                             const int32_t *mode, const float *keep, const uint8_t *const *mask, const uint64_t *seed,
+                             int64_t row_offset, void *stream) {
+    SSL_CHECK_ARG(x && out && mode && keep && seed, "ssl_node_drop: null argument");
+    SSL_CHECK_ARG(dim >= 4 && dim % 4 == 0 && n_views >= 1 && n_views <= SSL_MAX_VIEWS, "ssl_node_drop: bad shape");
+    NodeArgs na{};
+    for (int v = 0; v < n_views; ++v) {
+        na.mode[v] = mode[v]; na.keep[v] = keep[v]; na.seed[v] = seed[v];
+        na.mask[v] = mask ? mask[v] : nullptr;
+        SSL_CHECK_ARG(mode[v] != 2 || na.mask[v], "ssl_node_drop: injected mask missing for view %d", v);
+    }
+    const int64_t total = n * (dim / 4);
+    if (total == 0) return SSL_OK;
+    node_drop_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, out, n, dim, n_views, backward, na, (uint32_t)row_offset);
+    SSL_LAUNCH_CHECK("node_drop_kernel");
+    return SSL_OK;
+}

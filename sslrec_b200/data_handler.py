@@ -1,0 +1,135 @@
+"""Data side of the plugin surface: mirror of data_utils/data_handler_general_cf.py and
+data_utils/datasets_general_cf.py for graphs given as arrays (synthetic or loaded pickles).
+
+``DataHandlerGeneralCF(trn_mat, val_mat, tst_mat)`` exposes what models and trainer read from the
+reference's handler: ``torch_adj`` (sparse COO fp32 on ``configs['device']``), ``trn_mat``, the three
+dataloaders, and it sets ``configs['data']['user_num'/'item_num']`` in ``load_data`` (:81)."""
+from __future__ import annotations
+
+import numpy as np
+import scipy.sparse as sp
+import torch
+import torch.utils.data as data
+
+from .config import configs
+
+
+def normalized_adjacency(trn_mat: sp.coo_matrix):
+    """(rows, cols, vals, N) of D^-1/2 [[0,R],[R^T,0]] D^-1/2, deg = rowsum + 1e-10 in float64, fp32
+    values (data_handler_general_cf.py:37-73).  Vectorised; no scipy matrix products."""
+    n_user, n_item = trn_mat.shape
+    trn_mat = sp.coo_matrix(trn_mat)
+    key = np.unique(trn_mat.row.astype(np.int64) * n_item + trn_mat.col.astype(np.int64))
+    ur, ic = key // n_item, key % n_item + n_user
+    n = n_user + n_item
+    rows = np.concatenate([ur, ic])
+    cols = np.concatenate([ic, ur])
+    deg = np.bincount(rows, minlength=n).astype(np.float64) + 1e-10
+    dinv = np.power(deg, -0.5)
+    dinv[np.isinf(dinv)] = 0.0
+    vals = (dinv[cols] * dinv[rows]).astype(np.float32)
+    return rows, cols, vals, n
+
+
+class PairwiseTrnData(data.Dataset):
+    """(user, pos item, neg item) triples; negatives re-drawn every epoch by uniform rejection
+    sampling against the user's training positives (datasets_general_cf.py:6-26), vectorised."""
+
+    def __init__(self, coomat):
+        self.rows = coomat.row.astype(np.int32)
+        self.cols = coomat.col.astype(np.int32)
+        self.n_item = coomat.shape[1]
+        self._pos_keys = np.unique(self.rows.astype(np.int64) * self.n_item + self.cols.astype(np.int64))
+        self.negs = np.zeros(len(self.rows)).astype(np.int32)
+
+    def sample_negs(self):
+        rows64 = self.rows.astype(np.int64)
+        negs = np.random.randint(self.n_item, size=len(self.rows)).astype(np.int64)
+        todo = np.arange(len(self.rows))
+        while todo.size:
+            k = rows64[todo] * self.n_item + negs[todo]
+            pos = np.searchsorted(self._pos_keys, k)
+            hit = (pos < self._pos_keys.shape[0]) & (self._pos_keys[np.minimum(pos, self._pos_keys.shape[0] - 1)] == k)
+            todo = todo[hit]
+            negs[todo] = np.random.randint(self.n_item, size=todo.size)
+        self.negs = negs.astype(np.int32)
+
+    def __len__(self):
+        return len(self.rows)
+
+    def __getitem__(self, idx):
+        return self.rows[idx], self.cols[idx], self.negs[idx]
+
+
+class PairwiseWEpochFlagTrnData(PairwiseTrnData):
+    """NCL: a flag that is 1 on the very first sample and once every ``epoch_period`` epochs
+    (datasets_general_cf.py:28-44)."""
+
+    def __init__(self, coomat):
+        super().__init__(coomat)
+        self.epoch_flag_counter = -1
+        self.epoch_period = configs['model']['epoch_period']
+
+    def __getitem__(self, idx):
+        flag = 0
+        if self.epoch_flag_counter == -1:
+            flag = 1
+            self.epoch_flag_counter = 0
+        if idx == 0:
+            self.epoch_flag_counter += 1
+            if self.epoch_flag_counter % self.epoch_period == 0:
+                flag = 1
+        anc, pos, neg = super().__getitem__(idx)
+        return anc, pos, neg, flag
+
+
+class AllRankTstData(data.Dataset):
+    """Test users with their held-out positives and a dense train-mask row (datasets_general_cf.py:46-68)."""
+
+    def __init__(self, coomat, trn_mat):
+        self.csrmat = (sp.csr_matrix(trn_mat) != 0) * 1.0
+        coomat = sp.coo_matrix(coomat)
+        order = np.argsort(coomat.row, kind='stable')
+        rows, cols = coomat.row[order], coomat.col[order]
+        self.user_pos_lists = [list() for _ in range(coomat.shape[0])]
+        bounds = np.flatnonzero(np.diff(rows)) + 1
+        for u, chunk in zip(rows[np.concatenate([[0], bounds])] if len(rows) else [], np.split(cols, bounds) if len(rows) else []):
+            self.user_pos_lists[int(u)] = chunk.tolist()
+        self.test_users = np.unique(rows)
+
+    def __len__(self):
+        return len(self.test_users)
+
+    def __getitem__(self, idx):
+        pck_user = self.test_users[idx]
+        pck_mask = np.reshape(self.csrmat[pck_user].toarray(), [-1])
+        return pck_user, pck_mask
+
+
+class DataHandlerGeneralCF:
+    def __init__(self, trn_mat, val_mat=None, tst_mat=None):
+        self._mats = (sp.coo_matrix(trn_mat), val_mat, tst_mat)
+
+    def _make_torch_adj(self, mat):
+        rows, cols, vals, n = normalized_adjacency(mat)
+        idxs = torch.from_numpy(np.vstack([rows, cols]).astype(np.int64))
+        adj = torch.sparse_coo_tensor(idxs, torch.from_numpy(vals), (n, n), check_invariants=False)
+        return adj.to(configs['device'])
+
+    def load_data(self):
+        trn_mat, val_mat, tst_mat = self._mats
+        trn_mat = sp.coo_matrix((trn_mat != 0).astype(np.float32))
+        self.trn_mat = trn_mat
+        configs['data']['user_num'], configs['data']['item_num'] = trn_mat.shape
+        self.torch_adj = self._make_torch_adj(trn_mat)
+        if configs['train']['loss'] == 'pairwise':
+            trn_data = PairwiseTrnData(trn_mat)
+        elif configs['train']['loss'] == 'pairwise_with_epoch_flag':
+            trn_data = PairwiseWEpochFlagTrnData(trn_mat)
+        else:
+            raise NotImplementedError(configs['train']['loss'])
+        self.train_dataloader = data.DataLoader(trn_data, batch_size=configs['train']['batch_size'], shuffle=True, num_workers=0)
+        if val_mat is not None:
+            self.valid_dataloader = data.DataLoader(AllRankTstData(val_mat, trn_mat), batch_size=configs['test']['batch_size'], shuffle=False, num_workers=0)
+        if tst_mat is not None:
+            self.test_dataloader = data.DataLoader(AllRankTstData(tst_mat, trn_mat), batch_size=configs['test']['batch_size'], shuffle=False, num_workers=0)

@@ -1,0 +1,713 @@
+"""Host-side orchestration of the sm_100a kernels: multi-view K-layer propagation (forward and
+the transposed backward), and the autograd plumbing that lets ``cal_loss`` read like the
+reference's while every gradient is accumulated in place by the kernels.
+
+Gradient plumbing ("sinks").  ``propagate()`` returns a :class:`PropState` holding the
+interleaved embeddings ``E [N, V, d]`` (not autograd tensors) and a 0-d ``token`` that *is* an
+autograd output of the propagation node.  Loss functions take row references into a state
+(:class:`Rows`), depend on its token, and in their backward add their gradient rows straight into
+the state's sink buffers (``G_sum``, ``G_layer[k]``, ``G_e0``) with the kernels' atomics; they
+hand autograd only a zero for the token.  Autograd's ordering then guarantees the propagation
+node's backward runs after every loss wrote its rows; it walks the layers with the transposed
+SpMM (same CSR, mask key swapped) and returns d user_embeds / d item_embeds.  No [N, V, d]
+gradient is ever materialised per loss term or added by torch.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import PropArgs, check, lib
+from .graph import GraphPlan
+
+LOG2E = 1.4426950408889634
+
+
+def _stream(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _require_cuda(t: torch.Tensor, what: str):
+    if not t.is_cuda:
+        raise RuntimeError(f'sslrec_b200: {what} must live on a CUDA device (got {t.device}); there is no CPU path')
+    if t.dtype != torch.float32:
+        raise RuntimeError(f'sslrec_b200: {what} must be float32')
+
+
+def ceil_to(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+class KernelTimer:
+    """Optional CUDA-event brackets around the dominant kernels (bench.py's roofline numbers are
+    measured live with these, on the launching stream).  Off unless ``engine.TIMER`` is set."""
+
+    def __init__(self):
+        self.records = []          # (name, meta, start_event, end_event)
+
+    def summary(self):
+        out = {}
+        for name, meta, a, b in self.records:
+            e = out.setdefault(name, dict(ms=0.0, launches=0, meta=meta))
+            e['ms'] += a.elapsed_time(b)
+            e['launches'] += 1
+        return out
+
+
+TIMER: Optional[KernelTimer] = None
+
+
+class _timed:
+    def __init__(self, name, meta=None):
+        self.name, self.meta = name, meta
+
+    def __enter__(self):
+        if TIMER is not None:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+
+    def __exit__(self, *exc):
+        if TIMER is not None:
+            b = torch.cuda.Event(enable_timing=True)
+            b.record()
+            TIMER.records.append((self.name, self.meta, self.a, b))
+        return False
+
+
+# ------------------------------------------------------------------------------------------------
+# view specifications
+# ------------------------------------------------------------------------------------------------
+
+@dataclass
+class ViewSpec:
+    """One augmented view of the propagation (mirrors the reference augmentors).
+
+    edge_mode   0 none | 1 in-kernel RNG keep test | 2 injected CSR-order uint8 mask(s)
+    edge_masks  mode 2: one tensor (same mask for every layer: lightgcn.py:36-37, sgl.py:27-28) or a
+                list with one tensor per layer (hccf.py:47)
+    per_layer_edges  mode 1: redraw the mask at every layer (HCCF) instead of once per forward
+    scale       multiplier of kept values (1/keep for EdgeDrop(resize_val=True))
+    noise_mode  0 none | 1 in-kernel RNG | 2 injected per-layer [N, d] uniforms (``noise_u``)
+    node_mode   0 none | 1 RNG | 2 injected [N] uint8 mask (``node_mask``): NodeDrop on E0
+    """
+    edge_mode: int = 0
+    keep: float = 1.0
+    scale: float = 1.0
+    edge_masks: object = None
+    per_layer_edges: bool = False
+    noise_mode: int = 0
+    noise_u: Optional[Sequence[torch.Tensor]] = None
+    node_mode: int = 0
+    node_keep: float = 1.0
+    node_mask: Optional[torch.Tensor] = None
+    seed: int = 0
+
+    def edge_mask_for(self, layer: int) -> Optional[torch.Tensor]:
+        if self.edge_mode != 2:
+            return None
+        if isinstance(self.edge_masks, (list, tuple)):
+            return self.edge_masks[layer - 1]
+        return self.edge_masks
+
+
+def splitmix64(x: int) -> int:
+    x = (x + 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
+    z = x
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
+    return z ^ (z >> 31)
+
+
+class SeedStream:
+    """Per-model stream of 64-bit kernel seeds derived from the training seed (``train.seed``)."""
+
+    def __init__(self, seed: int):
+        self.state = splitmix64(int(seed) & 0xFFFFFFFFFFFFFFFF)
+
+    def next(self) -> int:
+        self.state = splitmix64(self.state)
+        return self.state
+
+
+# ------------------------------------------------------------------------------------------------
+# propagation
+# ------------------------------------------------------------------------------------------------
+
+class Rows:
+    """Reference to the rows [off, off+n) of view ``v`` of a [*, V, d] (or [*, d]) fp32 tensor, plus
+    where their gradient goes (a sink of the same shape, created zeroed on first use)."""
+
+    def __init__(self, base: torch.Tensor, v: int, n_views: int, off: int, n: int, dim: int,
+                 sink_get=None, token: Optional[torch.Tensor] = None):
+        self.base, self.v, self.n_views, self.off, self.n, self.dim = base, v, n_views, off, n, dim
+        self.sink_get, self.token = sink_get, token
+
+    @property
+    def stride(self) -> int:
+        return self.n_views * self.dim
+
+    @property
+    def ptr(self) -> int:
+        return self.base.data_ptr() + 4 * ((self.off * self.n_views + self.v) * self.dim)
+
+    def grad_ptr(self) -> Optional[int]:
+        if self.sink_get is None:
+            return None
+        g = self.sink_get()
+        return g.data_ptr() + 4 * ((self.off * self.n_views + self.v) * self.dim)
+
+    def dense(self) -> torch.Tensor:
+        """A strided torch view of the referenced rows (for inspection / tests)."""
+        b = self.base.view(-1, self.n_views, self.dim)
+        return b[self.off:self.off + self.n, self.v, :]
+
+    @staticmethod
+    def constant(t: torch.Tensor) -> 'Rows':
+        _require_cuda(t, 'constant rows')
+        t = t.contiguous()
+        return Rows(t, 0, 1, 0, t.shape[0], t.shape[1])
+
+
+class PropState:
+    """Result of one multi-view propagation (see module docstring)."""
+
+    def __init__(self, prop: 'Propagation', e0: torch.Tensor, n_user: int):
+        self.prop, self.e0, self.n_user = prop, e0, n_user
+        self.n, self.dim, self.n_views = e0.shape[0], e0.shape[1], len(prop.views)
+        self.E: Optional[torch.Tensor] = None
+        self.layers: Dict[int, torch.Tensor] = {}
+        self.token: Optional[torch.Tensor] = None
+        self._g_sum = None
+        self._g_layers: Dict[int, torch.Tensor] = {}
+        self._g_e0 = None
+
+    # ---- sinks -------------------------------------------------------------------------------
+    def g_sum(self) -> torch.Tensor:
+        if self._g_sum is None:
+            self._g_sum = torch.zeros_like(self.E)
+        return self._g_sum
+
+    def g_layer(self, k: int) -> torch.Tensor:
+        if k == 0:
+            return self.g_e0()
+        if k not in self._g_layers:
+            self._g_layers[k] = torch.zeros_like(self.layers[k])
+        return self._g_layers[k]
+
+    def g_e0(self) -> torch.Tensor:
+        if self._g_e0 is None:
+            self._g_e0 = torch.zeros_like(self.e0)
+        return self._g_e0
+
+    # ---- row references ------------------------------------------------------------------------
+    def _rows(self, which, v: int, off: int, n: int) -> Rows:
+        if which == 'sum':
+            return Rows(self.E, v, self.n_views, off, n, self.dim, self.g_sum, self.token)
+        k = int(which)
+        if k == 0:           # layer 0 is E0 itself (ncl.py:75)
+            return Rows(self.e0, 0, 1, off, n, self.dim, self.g_e0, self.token)
+        return Rows(self.layers[k], v, self.n_views, off, n, self.dim, lambda: self.g_layer(k), self.token)
+
+    def users(self, v: int = 0, which='sum') -> Rows:
+        return self._rows(which, v, 0, self.n_user)
+
+    def items(self, v: int = 0, which='sum') -> Rows:
+        return self._rows(which, v, self.n_user, self.n - self.n_user)
+
+    def all_nodes(self, v: int = 0, which='sum') -> Rows:
+        return self._rows(which, v, 0, self.n)
+
+
+class Propagation:
+    """K-layer LightGCN-family propagation of several augmented views in one pass per layer.
+
+    E_v = sum_{k=0..sum_layers} X_k^(v),  X_0^(v) = nodedrop_v(E0),  X_k^(v) = perturb_v(A_v X_{k-1}^(v)).
+    ``n_layers`` may exceed ``sum_layers`` (NCL runs max(L, 2*high_order) layers, ncl.py:36) and
+    ``keep_layers`` lists layer outputs that losses read (and send gradients to).
+    """
+
+    def __init__(self, plan: GraphPlan, views: Sequence[ViewSpec], n_layers: int, sum_layers: Optional[int] = None,
+                 keep_layers: Sequence[int] = (), noise_eps: float = 0.0, comm=None):
+        self.plan, self.views = plan, list(views)
+        self.n_layers = int(n_layers)
+        self.sum_layers = self.n_layers if sum_layers is None else int(sum_layers)
+        self.keep_layers = set(int(k) for k in keep_layers)
+        self.noise_eps = float(noise_eps)
+        self.comm = comm       # row-sharded multi-GPU: object with .allgather_rows(local [n_loc, V, d]) -> full
+        if not 1 <= len(self.views) <= _lib.MAX_VIEWS:
+            raise ValueError('1..%d views' % _lib.MAX_VIEWS)
+        if self.sum_layers > self.n_layers or self.sum_layers + 1 > _lib.MAX_SUM_SRC + 1:
+            raise ValueError('sum_layers out of range')
+        self.any_node = any(v.node_mode != 0 for v in self.views)
+
+    # ---- argument block ------------------------------------------------------------------------
+    def _args(self, dim: int, layer: int, transpose: bool) -> PropArgs:
+        a = PropArgs()
+        a.dim, a.n_views, a.transpose = dim, len(self.views), int(transpose)
+        a.noise_eps = self.noise_eps
+        a.noise_stream_id = layer
+        per_layer = any(v.per_layer_edges for v in self.views)
+        a.edge_stream_id = layer if per_layer else 0
+        for i, v in enumerate(self.views):
+            a.edge_mode[i] = v.edge_mode
+            a.edge_keep[i] = v.keep
+            a.edge_scale[i] = v.scale
+            a.seed[i] = v.seed
+            m = v.edge_mask_for(layer)
+            a.edge_mask[i] = _ptr(m)
+            if not transpose:
+                a.noise_mode[i] = v.noise_mode
+                if v.noise_mode == 2:
+                    a.noise_u[i] = _ptr(v.noise_u[layer - 1])
+        return a
+
+    def _launch(self, a: PropArgs, ref: torch.Tensor):
+        name = 'prop_bwd' if a.transpose else 'prop_fwd'
+        with torch.cuda.device(ref.device), _timed(name, dict(views=a.n_views, in_views=a.in_views, dim=a.dim)):
+            check(lib.ssl_propagate_layer(self.plan.handle, C.byref(a), _stream(ref)), 'ssl_propagate_layer')
+
+    def _node_drop(self, x: torch.Tensor, out: torch.Tensor, backward: bool):
+        V = len(self.views)
+        mode = (C.c_int32 * V)(*[v.node_mode for v in self.views])
+        keep = (C.c_float * V)(*[v.node_keep for v in self.views])
+        masks = (C.c_void_p * V)(*[_ptr(v.node_mask) for v in self.views])
+        seeds = (C.c_uint64 * V)(*[v.seed for v in self.views])
+        n = out.shape[0] if backward else x.shape[0]
+        with torch.cuda.device(x.device):
+            check(lib.ssl_node_drop(x.data_ptr(), out.data_ptr(), n, x.shape[-1], V, int(backward), mode, keep, masks, seeds,
+                                    self.plan.row_offset, _stream(x)), 'ssl_node_drop')
+
+    def _gather(self, local: torch.Tensor) -> torch.Tensor:
+        return local if self.comm is None else self.comm.allgather_rows(local)
+
+    # ---- forward -------------------------------------------------------------------------------
+    def forward(self, e0: torch.Tensor, n_user: int) -> PropState:
+        """e0: the full [N, d] table (every rank holds all of it; rows are sharded for compute)."""
+        _require_cuda(e0, 'embedding table')
+        if not e0.is_contiguous():
+            raise RuntimeError('embedding table must be contiguous')
+        st = PropState(self, e0, n_user)
+        N, d, V = e0.shape[0], e0.shape[1], len(self.views)
+        r0, nl = self.plan.row_offset, self.plan.n_rows
+        opts = dict(device=e0.device, dtype=torch.float32)
+        if self.any_node:
+            x0 = torch.empty(N, V, d, **opts)
+            self._node_drop(e0, x0, backward=False)
+            x_prev, in_views = x0, V
+            srcs = [(x0, V)]
+        else:
+            x_prev, in_views = e0, 1
+            srcs = [(e0, 1)]
+        st.x0 = x_prev
+        E_loc = None
+        for k in range(1, self.n_layers + 1):
+            a = self._args(d, k, transpose=False)
+            a.in_views = in_views
+            a.x_in = x_prev.data_ptr()
+            need_out = (k < self.n_layers) or (k in self.keep_layers)
+            x_out = torch.empty(nl, V, d, **opts) if need_out else None
+            a.x_out = _ptr(x_out)
+            if k == self.sum_layers:
+                E_loc = torch.empty(nl, V, d, **opts)
+                a.sum_out = E_loc.data_ptr()
+                a.n_sum_src = len(srcs)
+                for i, (s, sv) in enumerate(srcs):
+                    a.sum_src[i] = s.data_ptr() + 4 * (r0 * sv * d)
+                    a.sum_src_views[i] = sv
+            self._launch(a, e0)
+            if x_out is not None:
+                x_full = self._gather(x_out)
+                if k in self.keep_layers:
+                    st.layers[k] = x_full
+                if k < self.sum_layers:
+                    srcs.append((x_full, V))
+                x_prev, in_views = x_full, V
+        if self.sum_layers == 0:
+            raise ValueError('sum_layers must be >= 1')
+        st.E = self._gather(E_loc)
+        return st
+
+    # ---- backward ------------------------------------------------------------------------------
+    def backward(self, st: PropState) -> torch.Tensor:
+        """Consumes the sinks of ``st``; returns dE0 [N, d] (full; every rank computes its rows and
+        the row blocks are all-gathered)."""
+        e0 = st.e0
+        N, d, V = st.n, st.dim, st.n_views
+        r0, nl = self.plan.row_offset, self.plan.n_rows
+        opts = dict(device=e0.device, dtype=torch.float32)
+        L, S = self.n_layers, self.sum_layers
+
+        def residual(k: int) -> Optional[torch.Tensor]:
+            parts = []
+            if k <= S and st._g_sum is not None:
+                parts.append(st._g_sum)
+            if k >= 1 and k in st._g_layers:
+                parts.append(st._g_layers[k])
+            if not parts:
+                return None
+            return parts[0] if len(parts) == 1 else parts[0] + parts[1]
+
+        # D_k = total gradient w.r.t. X_k; start at the deepest layer that received any gradient
+        top = L
+        while top >= 1 and residual(top) is None:
+            top -= 1
+        g_e0 = st._g_e0
+        if top == 0:
+            d0 = residual(0)     # only X_0 got gradient (through the layer sum)
+            if d0 is None:
+                return g_e0 if g_e0 is not None else torch.zeros_like(e0)
+            out = d0.sum(1) if not self.any_node else self._node_bwd(d0, g_e0, e0)
+            if g_e0 is not None and not self.any_node:
+                out = out + g_e0
+            return out
+        D = residual(top)
+        for k in range(top, 0, -1):           # D_{k-1} = A_v^T D_k + residual(k-1)
+            a = self._args(d, k, transpose=True)
+            a.in_views = V
+            a.x_in = D.data_ptr()
+            res = residual(k - 1)
+            if res is not None:
+                a.residual = res.data_ptr() + 4 * (r0 * V * d)
+            last = (k == 1)
+            if last and not self.any_node:
+                out = torch.empty(nl, d, **opts)
+                a.sum_out, a.reduce_views = out.data_ptr(), 1
+                if g_e0 is not None:
+                    a.reg_src, a.reg_coef = g_e0.data_ptr() + 4 * (r0 * d), 1.0
+                self._launch(a, e0)
+                return self._gather_2d(out)
+            x_out = torch.empty(nl, V, d, **opts)
+            a.x_out = x_out.data_ptr()
+            self._launch(a, e0)
+            D = self._gather(x_out)
+        return self._node_bwd(D, g_e0, e0)
+
+    def _node_bwd(self, d0: torch.Tensor, g_e0: Optional[torch.Tensor], e0: torch.Tensor) -> torch.Tensor:
+        out = g_e0.clone() if g_e0 is not None else torch.zeros_like(e0)
+        self._node_drop(d0, out, backward=True)
+        return out
+
+    def _gather_2d(self, local: torch.Tensor) -> torch.Tensor:
+        if self.comm is None:
+            return local
+        return self.comm.allgather_rows(local.unsqueeze(1)).squeeze(1)
+
+
+class _PropFn(torch.autograd.Function):
+    """Autograd node of a propagation: inputs are the two embedding parameters, the only autograd
+    output is the 0-d token; E lives in the PropState."""
+
+    @staticmethod
+    def forward(ctx, user_e, item_e, prop: Propagation, e0: torch.Tensor, holder: dict):
+        st = prop.forward(e0, user_e.shape[0])
+        ctx.st = st
+        holder['state'] = st
+        return torch.zeros((), device=e0.device, dtype=torch.float32)
+
+    @staticmethod
+    def backward(ctx, g_token):
+        st = ctx.st
+        de0 = st.prop.backward(st)
+        nu = st.n_user
+        return de0[:nu], de0[nu:], None, None, None
+
+
+def propagate(prop: Propagation, user_e: torch.Tensor, item_e: torch.Tensor, e0: Optional[torch.Tensor] = None) -> PropState:
+    """Run the propagation.  ``e0`` is the flat [N, d] table the two parameters are views of (built by
+    a concat when they are not)."""
+    if e0 is None:
+        e0 = flat_table(user_e, item_e)
+    if torch.is_grad_enabled() and (user_e.requires_grad or item_e.requires_grad):
+        holder: dict = {}
+        token = _PropFn.apply(user_e, item_e, prop, e0, holder)
+        st = holder['state']
+        st.token = token
+        return st
+    return prop.forward(e0.detach(), user_e.shape[0])
+
+
+def flat_table(user_e: torch.Tensor, item_e: torch.Tensor) -> torch.Tensor:
+    """[N, d] table of both sides without a copy when the parameters are adjacent views of one
+    storage (FlatEmbeddings), else a concat (lightgcn.py:34)."""
+    ud, idt = user_e.detach(), item_e.detach()
+    if (ud.is_contiguous() and idt.is_contiguous() and ud.untyped_storage().data_ptr() == idt.untyped_storage().data_ptr()
+            and idt.data_ptr() == ud.data_ptr() + ud.numel() * 4 and ud.shape[1] == idt.shape[1]):
+        return torch.as_strided(ud, (ud.shape[0] + idt.shape[0], ud.shape[1]), (ud.shape[1], 1))
+    return torch.cat([ud, idt], 0)
+
+
+# ------------------------------------------------------------------------------------------------
+# losses
+# ------------------------------------------------------------------------------------------------
+
+def _i64(t: torch.Tensor, device) -> torch.Tensor:
+    if t.dtype != torch.int64 or t.device != device or not t.is_contiguous():
+        t = t.to(device=device, dtype=torch.int64).contiguous()
+    return t
+
+
+def _tokens(*rows: Rows) -> List[torch.Tensor]:
+    seen, out = set(), []
+    for r in rows:
+        if r is not None and r.token is not None and id(r.token) not in seen:
+            seen.add(id(r.token))
+            out.append(r.token)
+    return out
+
+
+def _bpr_fwd(users: Rows, items: Rows, ancs, poss, negs):
+    dev = users.base.device
+    B = ancs.numel()
+    loss_b = torch.empty(B, device=dev)
+    coef = torch.empty(B, device=dev)
+    out = torch.empty((), device=dev)
+    with torch.cuda.device(dev):
+        s = _stream(users.base)
+        check(lib.ssl_bpr_fwd(users.ptr, users.stride, items.ptr, items.stride, ancs.data_ptr(), poss.data_ptr(),
+                              negs.data_ptr(), B, users.dim, loss_b.data_ptr(), coef.data_ptr(), s), 'ssl_bpr_fwd')
+        check(lib.ssl_sum(loss_b.data_ptr(), B, 1.0, out.data_ptr(), s), 'ssl_sum')
+    return out, coef
+
+
+def _bpr_bwd(users: Rows, items: Rows, ancs, poss, negs, coef, g):
+    g = g.contiguous()
+    with torch.cuda.device(g.device):
+        check(lib.ssl_bpr_bwd(users.ptr, users.stride, items.ptr, items.stride, ancs.data_ptr(), poss.data_ptr(),
+                              negs.data_ptr(), ancs.numel(), users.dim, coef.data_ptr(), g.data_ptr(), 1.0,
+                              users.grad_ptr(), users.stride, items.grad_ptr(), items.stride, _stream(g)), 'ssl_bpr_bwd')
+
+
+class _BprFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, users: Rows, items: Rows, ancs, poss, negs, *tokens):
+        out, coef = _bpr_fwd(users, items, ancs, poss, negs)
+        ctx.pack = (users, items, ancs, poss, negs, coef, len(tokens))
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        users, items, ancs, poss, negs, coef, nt = ctx.pack
+        _bpr_bwd(users, items, ancs, poss, negs, coef, g)
+        zero = torch.zeros((), device=g.device)
+        return (None,) * 5 + (zero,) * nt
+
+
+def bpr_loss_sum(users: Rows, items: Rows, ancs, poss, negs) -> torch.Tensor:
+    """sum_b softplus(a.n - a.p) over gathered rows (lightgcn.py:48-52 + loss_utils.py:7-10)."""
+    dev = users.base.device
+    ancs, poss, negs = _i64(ancs, dev), _i64(poss, dev), _i64(negs, dev)
+    return _BprFn.apply(users, items, ancs, poss, negs, *_tokens(users, items))
+
+
+def choose_split(n_rtiles: int, n_ctiles: int, slots: int = 2 * 148) -> int:
+    """Number of chunks the streamed operand is cut into so that n_rtiles * n_split CTAs fill whole
+    waves of the resident-CTA slots (2 per SM at dim <= 64) with every CTA keeping >= 4 tiles."""
+    best, best_eff = 1, -1.0
+    max_split = max(1, min(n_ctiles // 4 if n_ctiles >= 4 else 1, 64))
+    for s in range(1, max_split + 1):
+        ctas = n_rtiles * s
+        waves = math.ceil(ctas / slots)
+        eff = ctas / (waves * slots)
+        if eff > best_eff + 1e-9:
+            best, best_eff = s, eff
+    return best
+
+
+def _nce_fwd(e1: Rows, e2: Rows, table: Rows, idx, idx2, tau, norm_mode, mean, deno_eps):
+    dev = table.base.device
+    d = table.dim
+    B, n = idx.numel(), table.n
+    Bp, npad = ceil_to(B, 64), ceil_to(n, 64)
+    f = dict(device=dev, dtype=torch.float32)
+    a_hat, a_t, rinv1 = torch.empty(Bp, d, **f), torch.empty(Bp // 64, d, 64, **f), torch.empty(B, **f)
+    p_hat, rinv2 = torch.empty(Bp, d, **f), torch.empty(B, **f)
+    t_hat, t_t, rinv_t = torch.empty(npad, d, **f), torch.empty(npad // 64, d, 64, **f), torch.empty(n, **f)
+    n_split = choose_split((B + 127) // 128, npad // 64)
+    rs_part, o_part = torch.empty(n_split, B, **f), torch.empty(n_split, B, d, **f)
+    rowsum, obar, loss_b, out = torch.empty(B, **f), torch.empty(B, d, **f), torch.empty(B, **f), torch.empty((), **f)
+    off = LOG2E / tau
+    with torch.cuda.device(dev):
+        s = _stream(table.base)
+        check(lib.ssl_rows_normalize(e1.ptr, e1.stride, idx.data_ptr(), B, d, norm_mode, off, a_hat.data_ptr(),
+                                     a_t.data_ptr(), rinv1.data_ptr(), s), 'ssl_rows_normalize(e1)')
+        check(lib.ssl_rows_normalize(e2.ptr, e2.stride, idx2.data_ptr(), B, d, norm_mode, 1.0, p_hat.data_ptr(), None,
+                                     rinv2.data_ptr(), s), 'ssl_rows_normalize(e2)')
+        check(lib.ssl_rows_normalize(table.ptr, table.stride, None, n, d, norm_mode, 1.0, t_hat.data_ptr(),
+                                     t_t.data_ptr(), rinv_t.data_ptr(), s), 'ssl_rows_normalize(table)')
+        with _timed('nce_gemm_fwd', dict(B=B, n=n, dim=d)):
+            check(lib.ssl_softmax_gemm(a_hat.data_ptr(), B, t_hat.data_ptr(), t_t.data_ptr(), n, d, None, off, n_split,
+                                       rs_part.data_ptr(), o_part.data_ptr(), s), 'ssl_softmax_gemm(fwd)')
+        check(lib.ssl_nce_finalize(rs_part.data_ptr(), o_part.data_ptr(), n_split, B, d, a_hat.data_ptr(), p_hat.data_ptr(),
+                                   tau, deno_eps * math.exp(-1.0 / tau), rowsum.data_ptr(), obar.data_ptr(),
+                                   loss_b.data_ptr(), s), 'ssl_nce_finalize')
+        check(lib.ssl_sum(loss_b.data_ptr(), B, (1.0 / B) if mean else 1.0, out.data_ptr(), s), 'ssl_sum')
+    saved = (e1, e2, table, idx, tau, mean, a_hat, a_t, p_hat, rinv1, rinv2, t_hat, rinv_t, rowsum, obar)
+    return out, saved
+
+
+def _nce_bwd(saved, g):
+    (e1, e2, table, idx, tau, mean, a_hat, a_t, p_hat, rinv1, rinv2, t_hat, rinv_t, rowsum, obar) = saved
+    dev, d = g.device, table.dim
+    B, n = idx.numel(), table.n
+    g = g.contiguous()
+    scale = (1.0 / B) if mean else 1.0
+    f = dict(device=dev, dtype=torch.float32)
+    with torch.cuda.device(dev):
+        s = _stream(g)
+        g1, g2, gt = e1.grad_ptr(), e2.grad_ptr(), table.grad_ptr()
+        if g1 is not None or g2 is not None:
+            check(lib.ssl_nce_bwd_rows(a_hat.data_ptr(), p_hat.data_ptr(), obar.data_ptr(), rinv1.data_ptr(), rinv2.data_ptr(),
+                                       idx.data_ptr(), B, d, tau, g.data_ptr(), scale, g1, e1.stride, g2, e2.stride, s),
+                  'ssl_nce_bwd_rows')
+        if gt is not None:
+            colscale = torch.empty(ceil_to(B, 64), **f)
+            check(lib.ssl_nce_colscale(rowsum.data_ptr(), B, g.data_ptr(), scale, colscale.data_ptr(), s), 'ssl_nce_colscale')
+            n_split = choose_split((n + 127) // 128, ceil_to(B, 64) // 64)
+            dt_part = torch.empty(n_split, n, d, **f)
+            with _timed('nce_gemm_bwd', dict(B=B, n=n, dim=d)):
+                check(lib.ssl_softmax_gemm(t_hat.data_ptr(), n, a_hat.data_ptr(), a_t.data_ptr(), B, d, colscale.data_ptr(),
+                                           LOG2E / tau, n_split, None, dt_part.data_ptr(), s), 'ssl_softmax_gemm(bwd)')
+            check(lib.ssl_nce_bwd_table(dt_part.data_ptr(), n_split, t_hat.data_ptr(), rinv_t.data_ptr(), n, d, gt,
+                                        table.stride, 1, s), 'ssl_nce_bwd_table')
+
+
+class _InfoNceFn(torch.autograd.Function):
+    """One InfoNCE term: rows e1[idx], e2[idx2] against all rows of ``table`` (loss_utils.py:30-39,
+    and :42-51 with norm_mode 1 / mean reduction / deno_eps)."""
+
+    @staticmethod
+    def forward(ctx, e1: Rows, e2: Rows, table: Rows, idx, idx2, tau, norm_mode, mean, deno_eps, *tokens):
+        out, ctx.saved_pack = _nce_fwd(e1, e2, table, idx, idx2, tau, norm_mode, mean, deno_eps)
+        ctx.nt = len(tokens)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        _nce_bwd(ctx.saved_pack, g)
+        zero = torch.zeros((), device=g.device)
+        return (None,) * 9 + (zero,) * ctx.nt
+
+
+def infonce_loss_sum(e1: Rows, e2: Rows, table: Rows, idx, temp: float, idx2=None) -> torch.Tensor:
+    """cal_infonce_loss on row references: sum_b [-(e1^.e2^)/temp + log sum_j exp(e1^.table^_j/temp)]."""
+    dev = table.base.device
+    idx = _i64(idx, dev)
+    idx2 = idx if idx2 is None else _i64(idx2, dev)
+    return _InfoNceFn.apply(e1, e2, table, idx, idx2, float(temp), 0, False, 0.0, *_tokens(e1, e2, table))
+
+
+# ---- the same kernels behind plain dense tensors (reference signatures; gradients are returned
+# ---- as ordinary dense tensors -- used by HCCF, whose hyper-graph branch lives in torch autograd)
+
+class _LocalSink:
+    def __init__(self, like: torch.Tensor):
+        self.like, self.buf = like, None
+
+    def __call__(self):
+        if self.buf is None:
+            self.buf = torch.zeros_like(self.like)
+        return self.buf
+
+
+def _dense_rows(t: torch.Tensor, with_grad: bool):
+    _require_cuda(t, 'loss input')
+    t = t.detach().contiguous()
+    sink = _LocalSink(t) if with_grad else None
+    return Rows(t, 0, 1, 0, t.shape[0], t.shape[1], sink), sink
+
+
+class _DenseBprFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, anc, pos, neg):
+        B = anc.shape[0]
+        ar = torch.arange(B, device=anc.device)
+        items = torch.cat([pos.detach(), neg.detach()], 0)
+        users, su = _dense_rows(anc, True)
+        items_r, si = _dense_rows(items, True)
+        out, coef = _bpr_fwd(users, items_r, ar, ar, ar + B)
+        ctx.pack = (users, items_r, ar, coef, su, si, B)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        users, items_r, ar, coef, su, si, B = ctx.pack
+        _bpr_bwd(users, items_r, ar, ar, ar + B, coef, g)
+        gi = si()
+        return su(), gi[:B], gi[B:]
+
+
+class _DenseInfoNceFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, e1, e2, table, idx, idx2, tau, norm_mode, mean, deno_eps, shared_table):
+        r1, s1 = _dense_rows(e1, ctx.needs_input_grad[0])
+        if shared_table:                      # e2 rows are rows of the table itself (spec_nodes)
+            rt, st_ = _dense_rows(table, ctx.needs_input_grad[2])
+            r2, s2 = rt, st_
+        else:
+            r2, s2 = _dense_rows(e2, ctx.needs_input_grad[1])
+            rt, st_ = _dense_rows(table, ctx.needs_input_grad[2])
+        out, ctx.saved_pack = _nce_fwd(r1, r2, rt, idx, idx2, tau, norm_mode, mean, deno_eps)
+        ctx.sinks = (s1, s2, st_, shared_table)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        _nce_bwd(ctx.saved_pack, g)
+        s1, s2, st_, shared = ctx.sinks
+        g1 = s1() if s1 is not None else None
+        g2 = None if shared else (s2() if s2 is not None else None)
+        gt = st_() if st_ is not None else None
+        return g1, g2, gt, None, None, None, None, None, None, None
+
+
+def dense_bpr_loss_sum(anc, pos, neg):
+    return _DenseBprFn.apply(anc, pos, neg)
+
+
+def dense_infonce_loss_sum(e1, e2, all2, temp):
+    """cal_infonce_loss(embeds1 [B,d], embeds2 [B,d], all_embeds2 [N,d], temp) -- loss_utils.py:30-39."""
+    B = e1.shape[0]
+    ar = torch.arange(B, device=e1.device)
+    return _DenseInfoNceFn.apply(e1, e2, all2, ar, ar, float(temp), 0, False, 0.0, False)
+
+
+def dense_infonce_spec_nodes_mean(embeds1, embeds2, nodes, temp):
+    """cal_infonce_loss_spec_nodes(embeds1 [N,d], embeds2 [N,d], nodes, temp) -- loss_utils.py:42-51."""
+    nodes = _i64(nodes, embeds2.device)
+    return _DenseInfoNceFn.apply(embeds1, embeds2, embeds2, nodes, nodes, float(temp), 1, True, 1e-8, True)
+
+
+class _SumSqFn(torch.autograd.Function):
+    """reg_params over the flat table: value by a deterministic reduction; the gradient 2 g W is
+    added into the state's G_e0 sink (consumed by the last backward layer's epilogue)."""
+
+    @staticmethod
+    def forward(ctx, st, e0, *tokens):
+        out = torch.empty((), device=e0.device, dtype=torch.float32)
+        with torch.cuda.device(e0.device):
+            check(lib.ssl_sumsq(e0.data_ptr(), e0.numel(), out.data_ptr(), _stream(e0)), 'ssl_sumsq')
+        ctx.st, ctx.e0, ctx.n_in = st, e0, len(tokens)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        st, e0 = ctx.st, ctx.e0
+        g = g.contiguous()
+        sink = st.g_e0()
+        with torch.cuda.device(g.device):
+            check(lib.ssl_axpy(e0.data_ptr(), sink.data_ptr(), e0.numel(), g.data_ptr(), 2.0, _stream(g)), 'ssl_axpy')
+        return (None, None) + (torch.zeros((), device=g.device),) * ctx.n_in
+
+
+def table_sumsq(st: PropState) -> torch.Tensor:
+    """sum ||W||^2 of the embedding table a PropState was built from (loss_utils.py:20-24)."""
+    return _SumSqFn.apply(st, st.e0, *([st.token] if st.token is not None else []))

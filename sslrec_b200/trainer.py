@@ -1,0 +1,110 @@
+"""Trainer -- mirror of the base ``Trainer`` of trainer/trainer.py:39-162 for the surface the hot
+path needs: ``create_optimizer`` (Adam only, :45-49; here the fused kernel), ``train_epoch`` (:51-84,
+same loop: sample_negs, zero_grad, cal_loss, loss.item(), backward, step, per-term float()) and
+``evaluate`` (:139-152 + metrics.py:82-127 with the native top-k)."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from ._lib import check, lib
+from .config import configs
+from .optim import FusedAdam
+
+
+def init_seed():
+    """trainer/trainer.py:26-36."""
+    t = configs.get('train', {})
+    if t.get('reproducible', False):
+        seed = t['seed']
+        np.random.seed(seed)
+        torch.manual_seed(seed)
+        if torch.cuda.is_available():
+            torch.cuda.manual_seed_all(seed)
+
+
+class Trainer(object):
+    def __init__(self, data_handler, logger=None):
+        self.data_handler = data_handler
+        self.logger = logger
+
+    def create_optimizer(self, model):
+        optim_config = configs['optimizer']
+        if optim_config['name'] == 'adam':
+            self.optimizer = FusedAdam(model.parameters(), lr=optim_config['lr'], weight_decay=optim_config['weight_decay'])
+        else:
+            raise NotImplementedError("only 'adam' is supported (trainer.py:47)")
+
+    def train_epoch(self, model, epoch_idx):
+        train_dataloader = self.data_handler.train_dataloader
+        train_dataloader.dataset.sample_negs()
+        loss_log_dict = {}
+        ep_loss = 0
+        model.train()
+        for _, tem in enumerate(train_dataloader):
+            self.optimizer.zero_grad()
+            batch_data = list(map(lambda x: x.long().to(configs['device']), tem))
+            loss, loss_dict = model.cal_loss(batch_data)
+            ep_loss += loss.item()
+            loss.backward()
+            self.optimizer.step()
+            for loss_name in loss_dict:
+                _loss_val = float(loss_dict[loss_name]) / len(train_dataloader)
+                loss_log_dict[loss_name] = loss_log_dict.get(loss_name, 0.0) + _loss_val
+        if self.logger is not None:
+            self.logger.log_loss(epoch_idx, loss_log_dict, save_to_log=configs['train'].get('log_loss', True))
+        return ep_loss, loss_log_dict
+
+    def train(self, model):
+        self.create_optimizer(model)
+        for epoch_idx in range(configs['train']['epoch']):
+            self.train_epoch(model, epoch_idx)
+            if epoch_idx % configs['train']['test_step'] == 0 and hasattr(self.data_handler, 'valid_dataloader'):
+                self.evaluate(model, epoch_idx)
+        return model
+
+    @torch.no_grad()
+    def evaluate(self, model, epoch_idx=None, loader=None):
+        """All-rank evaluation: full_predict -> top-max(k) on device -> recall / ndcg on host
+        (metrics.py:82-127, :11-45)."""
+        model.eval()
+        loader = loader or getattr(self.data_handler, 'valid_dataloader', None) or self.data_handler.test_dataloader
+        ks = configs['test']['k']
+        metrics = configs['test']['metrics']
+        result = {m: np.zeros(len(ks)) for m in metrics}
+        ds = loader.dataset
+        n_users = len(ds.test_users)
+        for tem in loader:
+            users = tem[0].numpy().tolist()
+            batch_data = list(map(lambda x: x.long().to(configs['device']), tem))
+            preds = model.full_predict(batch_data)
+            top = topk(preds, max(ks)).cpu().numpy()
+            for bi, u in enumerate(users):
+                truth = ds.user_pos_lists[u]
+                hit = np.isin(top[bi], truth).astype(np.float64)
+                for ki, k in enumerate(ks):
+                    if 'recall' in result:
+                        result['recall'][ki] += hit[:k].sum() / len(truth) / n_users
+                    if 'ndcg' in result:
+                        idcg = (1.0 / np.log2(np.arange(2, min(k, len(truth)) + 2))).sum()
+                        result['ndcg'][ki] += (hit[:k] / np.log2(np.arange(2, k + 2))).sum() / idcg / n_users
+                    if 'precision' in result:
+                        result['precision'][ki] += hit[:k].sum() / k / n_users
+        if self.logger is not None:
+            self.logger.log_eval(result, ks, data_type='Validation set', epoch_idx=epoch_idx)
+        return result
+
+
+def topk(preds: torch.Tensor, k: int, return_values: bool = False):
+    """The k largest scores per row, descending, ties -> lower item id (replaces torch.topk at
+    metrics.py:108)."""
+    if not preds.is_cuda:
+        raise RuntimeError('sslrec_b200.topk: CUDA tensors only')
+    preds = preds.contiguous()
+    n_b, n_item = preds.shape
+    idx = torch.empty(n_b, k, device=preds.device, dtype=torch.int64)
+    val = torch.empty(n_b, k, device=preds.device, dtype=torch.float32)
+    with torch.cuda.device(preds.device):
+        check(lib.ssl_topk(preds.data_ptr(), n_b, n_item, k, idx.data_ptr(), val.data_ptr(),
+                           torch.cuda.current_stream(preds.device).cuda_stream), 'ssl_topk')
+    return (idx, val) if return_values else idx

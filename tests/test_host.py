@@ -1,0 +1,88 @@
+"""CPU-only checks of the host side: the C-ABI library loads and exports every symbol the header
+declares, the host logic that needs no GPU (config mirror, data handler, generators, seed streams)."""
+import os
+import re
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    import ctypes
+    from sslrec_b200 import _lib
+    hdr = open(os.path.join(ROOT, 'include', 'sslrec_b200.h')).read()
+    declared = set(re.findall(r'SSL_API\s+[\w\s\*]+?\b(ssl_\w+)\s*\(', hdr))
+    assert len(declared) >= 20
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert declared == set(_lib.EXPORTS)
+    assert _lib.lib.ssl_version() >= 100
+
+
+def test_prop_args_struct_matches_header_layout():
+    """ctypes mirror vs the C struct: compile a tiny C program against the header and compare sizeof/offsetof."""
+    import ctypes, subprocess, tempfile
+    from sslrec_b200 import _lib
+    src = '#include <stdio.h>\n#include <stddef.h>\n#include "sslrec_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu\\n", sizeof(ssl_prop_args), offsetof(ssl_prop_args, sum_src), offsetof(ssl_prop_args, edge_mask), offsetof(ssl_prop_args, seed), offsetof(ssl_prop_args, noise_stream_id));return 0;}'
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, 't.c'), 'w').write(src)
+        subprocess.run(['gcc', '-I', os.path.join(ROOT, 'include'), os.path.join(d, 't.c'), '-o', os.path.join(d, 't')], check=True)
+        out = subprocess.run([os.path.join(d, 't')], capture_output=True, text=True, check=True).stdout.split()
+    P = _lib.PropArgs
+    assert [int(x) for x in out] == [ctypes.sizeof(P), P.sum_src.offset, P.edge_mask.offset, P.seed.offset, P.noise_stream_id.offset]
+
+
+def test_normalized_adjacency_matches_oracle_bits():
+    from oracle import cf_oracle as O
+    from oracle import inputs
+    from sslrec_b200.data_handler import normalized_adjacency
+    case = inputs.make_case('small')
+    trn = sp.coo_matrix((np.ones(len(case['rows'])), (case['rows'], case['cols'])), shape=(case['n_user'], case['n_item']))
+    rows, cols, vals, n = normalized_adjacency(trn)
+    adj = O.normalized_adjacency(case['rows'], case['cols'], case['n_user'], case['n_item'])
+    o = np.lexsort((cols, rows))
+    assert n == adj.n and np.array_equal(rows[o], adj.rows) and np.array_equal(cols[o], adj.cols)
+    assert np.array_equal(vals[o].view(np.uint32), adj.vals.view(np.uint32))
+
+
+def test_vectorised_negative_sampler():
+    from sslrec_b200.config import default_config, load_config
+    from sslrec_b200.data_handler import PairwiseTrnData
+    from oracle import inputs
+    load_config(base=default_config('lightgcn'), device='cpu')
+    case = inputs.make_case('small')
+    trn = sp.coo_matrix((np.ones(len(case['rows'])), (case['rows'], case['cols'])), shape=(case['n_user'], case['n_item']))
+    ds = PairwiseTrnData(trn)
+    np.random.seed(1)
+    ds.sample_negs()
+    pos = set(zip(case['rows'].tolist(), case['cols'].tolist()))
+    assert all((u, j) not in pos for u, j in zip(ds.rows.tolist(), ds.negs.tolist()))
+    assert ds.negs.min() >= 0 and ds.negs.max() < case['n_item'] and len(set(ds.negs.tolist())) > case['n_item'] // 2
+
+
+def test_synthetic_graph_generator_is_deterministic_and_exact():
+    from sslrec_b200.datagen import bipartite_graph
+    r1, c1 = bipartite_graph(2000, 1500, 30000, seed=5, zipf_alpha=0.5)
+    r2, c2 = bipartite_graph(2000, 1500, 30000, seed=5, zipf_alpha=0.5)
+    assert np.array_equal(r1, r2) and np.array_equal(c1, c2) and len(r1) == 30000
+    assert len(set(zip(r1.tolist(), c1.tolist()))) == 30000
+    assert r1.max() < 2000 and c1.max() < 1500
+
+
+def test_models_refuse_to_run_without_cuda():
+    from sslrec_b200 import engine as E
+    with pytest.raises(RuntimeError, match='CUDA'):
+        E._require_cuda(torch.zeros(2, 4), 'table')
+
+
+def test_choose_split_fills_waves():
+    from sslrec_b200.engine import choose_split
+    assert choose_split(32, 1309) == 37          # 32 * 37 = 1184 = 4 waves of 296 CTA slots
+    assert choose_split(32, 1) == 1
+    s = choose_split(655, 64)
+    assert 1 <= s <= 16 and (655 * s) / (296 * -(-655 * s // 296)) > 0.95
