@@ -73,48 +73,49 @@ def make_batches(rows, cols, n_item, count, seed=2023):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
-    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
-         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+    """SM clock / throttle reasons read through NVML from the benchmarking thread itself WHILE the GPU
+    works through the enqueued steps (a polling nvidia-smi subprocess perturbed the timed region by
+    25 % in round 1, so no subprocess, no sampler thread)."""
+    REASONS = {0x8: 'hw_slowdown', 0x40: 'hw_thermal_slowdown', 0x20: 'sw_thermal_slowdown', 0x4: 'sw_power_cap',
+               0x80: 'hw_power_brake_slowdown'}
 
     def __init__(self, gpu_index):
-        self.gpu, self.proc, self.lines = gpu_index, None, []
-
-    def start(self):
+        self.sm, self.mx, self.power, self.reasons, self.h = [], None, [], set(), None
         try:
-            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '100',
-                                          '-i', str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._pump, daemon=True)
-            self.t.start()
-        except OSError:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception as e:      # noqa: BLE001
+            self.err = repr(e)
 
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.lines.append(line)
-
-    def stop(self):
-        if self.proc is None:
-            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
-        self.proc.terminate()
+    def sample(self):
+        if self.h is None:
+            return
+        nv = self.nv
         try:
-            self.proc.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(',')]
-            if len(f) < 8:
-                continue
-            try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[4:8]):
-                if v.lower().startswith('active'):
-                    reasons.add(name)
-        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
-                'reasons': sorted(reasons), 'samples': len(sm)}
+            self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+            self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+            get = getattr(nv, 'nvmlDeviceGetCurrentClocksEventReasons', None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+            bits = int(get(self.h))
+            for bit, name in self.REASONS.items():
+                if bits & bit:
+                    self.reasons.add(name)
+        except Exception as e:      # noqa: BLE001
+            self.err = repr(e)
+
+    def drain(self, event, period_s=0.02):
+        """Sample until ``event`` (recorded after the last timed step) has completed."""
+        while not event.query():
+            self.sample()
+            time.sleep(period_s)
+
+    def result(self):
+        if self.h is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvml unavailable: ' + getattr(self, 'err', '?')]}
+        return {'sm_mhz': float(np.median(self.sm)) if self.sm else None, 'sm_max_mhz': self.mx, 'reasons': sorted(self.reasons),
+                'samples': len(self.sm), 'power_w_max': max(self.power) if self.power else None}
 
 
 def measured_peaks():
@@ -132,13 +133,21 @@ def cpu_steps(model, hp, rows, cols, n_user, n_item, batches, budget_s, max_step
     from oracle import cf_oracle as O
     adj = O.normalized_adjacency(rows, cols, n_user, n_item)
     adj.reference_layout = True                      # the reference's column-sorted COO (data_handler_general_cf.py:69-72)
-    threads = os.cpu_count() or 1
-    torch.set_num_threads(threads)
     tr = O.CpuTrainer(model, adj, hp['embedding_size'], dict(hp, lr=1e-3))
     tb = [tuple(torch.from_numpy(b[i]) for i in range(3)) for b in batches]
     t_start = time.perf_counter()
-    for i in range(warmup):
-        tr.step(tb[i % len(tb)])
+    # all host threads, unless fewer are faster (torch's sparse COO addmm stops scaling early): one
+    # untimed step per candidate doubles as the warm-up
+    cands = sorted({os.cpu_count() or 1, min(os.cpu_count() or 1, 32)}, reverse=True)
+    best, threads = None, cands[0]
+    for c in cands[:max(1, warmup + 1)]:
+        torch.set_num_threads(c)
+        t0 = time.perf_counter()
+        tr.step(tb[0])
+        dt = time.perf_counter() - t0
+        if best is None or dt < best:
+            best, threads = dt, c
+    torch.set_num_threads(threads)
     times = []
     for i in range(max_steps):
         t0 = time.perf_counter()
@@ -228,6 +237,8 @@ def run_ours(args):
         opt.step()
         return loss
 
+    e2e_sampler = [None]
+
     def step_e2e(i):
         opt.zero_grad()
         b = host_batches[i].to(dev, non_blocking=True)           # trainer.py:64
@@ -235,8 +246,10 @@ def run_ours(args):
         v = loss.item()                                          # trainer.py:66 (D2H sync)
         loss.backward()
         opt.step()
+        if e2e_sampler[0] is not None and i % 4 == 0:
+            e2e_sampler[0].sample()                              # GPU is busy with the backward pass here
         for name in parts:                                       # trainer.py:72
-            float(parts[name])
+            float(parts[name].detach())
         return v
 
     def barrier():
@@ -244,22 +257,24 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn):
+    def timed(fn, inline_sampling=False):
         for i in range(W):
             fn(i)
         barrier()
-        sampler = ClockSampler(local_rank)
-        if rank == 0:
-            sampler.start()
+        sampler = ClockSampler(local_rank) if rank == 0 else None
+        e2e_sampler[0] = sampler if inline_sampling else None
         l0 = _lib.launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(K):
             fn(W + i)
         e1.record()
+        if sampler is not None and not inline_sampling:
+            sampler.drain(e1)                                    # the host is ahead of the GPU: sample while it works
         barrier()
+        e2e_sampler[0] = None
         launches = _lib.launch_count() - l0
-        clocks = sampler.stop() if rank == 0 else None
+        clocks = sampler.result() if rank == 0 else None
         ms = e0.elapsed_time(e1)
         if dist is not None:
             t = torch.tensor([ms], device=dev)
@@ -268,7 +283,7 @@ def run_ours(args):
         return ms / K, launches, clocks
 
     ms_res, launches, clocks = timed(step_resident)
-    ms_e2e, _, clocks_e2e = timed(step_e2e)
+    ms_e2e, _, clocks_e2e = timed(step_e2e, inline_sampling=True)
 
     # ---- live kernel timings (CUDA events on the launching stream) over K more steps ----
     engine.TIMER = engine.KernelTimer()
@@ -281,6 +296,7 @@ def run_ours(args):
     barrier()
     prof_ms = e0.elapsed_time(e1) / K
     summ = engine.TIMER.summary()
+    engine_launches = engine.TIMER.launches()
     engine.TIMER = None
     if rank != 0:
         if dist is not None:
@@ -290,46 +306,32 @@ def run_ours(args):
     peaks, peak_kind = measured_peaks()
     N, nnz, d = n_user + n_item, 2 * len(rows), hp['embedding_size']
     L = hp['layer_num']
-    # algorithmic bytes of one propagation launch: every stored entry moves V d-wide rows
-    # (4 V d bytes) + its (col, val) pair (8 bytes); every output row is written once per view
-    # (4 V d bytes) + its work item (16 bytes)
-    def prop_bytes(views, in_views):
-        gather_views = views if in_views == views else 1
-        return nnz * (4 * d * gather_views + 8) + N * (4 * d * views + 16)
-    prop_ms = prop_bytes_total = 0.0
-    prop_launches = 0
-    for name in ('prop_fwd', 'prop_bwd'):
-        if name in summ:
-            prop_ms += summ[name]['ms']
-            prop_launches += summ[name]['launches']
-    # per-launch bytes: recompute from the recorded metas
-    engine_records = summ
     views = 3 if model_name in ('simgcl', 'sgl') else 1
-    launches_per_step = prop_launches / K if K else 0
-    # forward layer 1 reads the shared [N, d] input; all other launches gather `views` rows per entry
-    bytes_per_step = 0.0
-    fwd_l, bwd_l = summ.get('prop_fwd', {'launches': 0})['launches'] / K, summ.get('prop_bwd', {'launches': 0})['launches'] / K
-    if fwd_l:
-        shared_first = model_name == 'simgcl'      # SGL / LightGCN(keep<1) mask per view -> no shared layer
-        bytes_per_step += prop_bytes(views, 1 if shared_first else 1) * 1 + prop_bytes(views, views) * (fwd_l - 1)
-        if not shared_first and views > 1:
-            bytes_per_step += nnz * 4 * d * (views - 1)   # masked layer 1 still fetches the shared row once per view
-    bytes_per_step += prop_bytes(views, views) * bwd_l
-    avg_prop_ms = prop_ms / prop_launches if prop_launches else float('nan')
-    avg_bytes = bytes_per_step / launches_per_step if launches_per_step else float('nan')
-    achieved = avg_bytes / (avg_prop_ms * 1e-3) / 1e9 if prop_launches else None
-    roofline = {'kernel': 'prop_kernel (ssl_propagate_layer, fwd+bwd launches)', 'bound': 'hbm', 'achieved': achieved,
-                'peak': peaks['hbm_gbs'], 'peak_kind': peak_kind + ' (burst copy)', 'unit': 'GB/s',
+    launches_all = engine_launches
+
+    def prop_alg_bytes(m):
+        """Algorithmic bytes of one propagation launch: per stored entry its (col, val) pair
+        (8 B) and one d-wide row per gathered view (4 d B); per output row its work item (16 B), every d-wide
+        row the epilogue must read (residual, layer-sum sources, regulariser row) and every row it writes."""
+        row = 4 * m['dim']
+        b = m['nnz'] * (8 + row * m['gather_views'])
+        per_row = 16 + (row * m['views'] if m['residual'] else 0) + sum(row * sv for sv in m['sum_src']) + (row if m['reg_src'] else 0)
+        per_row += row * m['views'] if m['x_out'] else 0
+        per_row += (row if m['reduce_views'] else row * m['views']) if m['sum_out'] else 0
+        return b + m['rows'] * per_row
+    prop = [(m, ms) for name, m, ms in launches_all if name in ('prop_fwd', 'prop_bwd')]
+    prop_ms = sum(ms for _, ms in prop)
+    prop_bytes = sum(prop_alg_bytes(m) for m, _ in prop)
+    achieved = prop_bytes / (prop_ms * 1e-3) / 1e9 if prop else None
+    roofline = {'kernel': 'prop_kernel (ssl_propagate_layer; all forward + transposed-backward launches of the timed steps)',
+                'bound': 'hbm', 'achieved': achieved, 'peak': peaks['hbm_gbs'], 'peak_kind': peak_kind + ' (burst copy)', 'unit': 'GB/s',
                 'frac': (achieved / peaks['hbm_gbs']) if achieved else None, 'traffic': None,
-                'avg_launch_ms': avg_prop_ms, 'alg_bytes_per_launch': avg_bytes, 'launches_per_step': launches_per_step,
-                'share_of_step': prop_ms / K / prof_ms if prof_ms else None,
-                'note': 'tables (41 MB/view) are L2-resident on this graph: achieved counts L2 hits, see DESIGN.md'}
+                'avg_launch_ms': prop_ms / len(prop) if prop else None, 'alg_bytes_per_launch': prop_bytes / len(prop) if prop else None,
+                'launches_per_step': len(prop) / K, 'share_of_step': prop_ms / K / prof_ms if prof_ms else None,
+                'note': 'the 41 MB/view tables of this graph fit the 126 MB L2, so achieved counts L2 hits and can exceed the HBM peak; '
+                        'traffic (ncu dram bytes) is in profiles/'}
     # the dense InfoNCE contraction, reported separately against the FP32 FMA pipe (not HBM-bound)
     nce_ms = sum(summ[k]['ms'] for k in ('nce_gemm_fwd', 'nce_gemm_bwd') if k in summ)
-    nce_flops = 0.0
-    for k in ('nce_gemm_fwd', 'nce_gemm_bwd'):
-        if k in summ:
-            pass
     terms = {'simgcl': [n_user, n_item], 'sgl': [n_user, n_item, n_item]}.get(model_name, [])
     nce_flops_step = sum(8.0 * BATCH * n * d for n in terms)          # fwd 4 B N d + bwd 4 B N d per term
     sm_mhz = (clocks or {}).get('sm_mhz') or 1965.0
@@ -361,7 +363,7 @@ def run_ours(args):
         'gpu_launches': launches, 'gpu_launches_per_step': launches / K,
         'embeddings_propagated_per_sec': emb_per_step * value,
         'roofline': roofline, 'roofline_infonce': roofline_nce, 'cpu_baseline': cpu,
-        'clocks': clocks, 'kernel_ms_per_step': {k: v['ms'] / K for k, v in summ.items()}, 'profiled_ms_per_step': prof_ms,
+        'clocks': clocks, 'clocks_e2e': clocks_e2e, 'kernel_ms_per_step': {k: v['ms'] / K for k, v in summ.items()}, 'profiled_ms_per_step': prof_ms,
     }
     print(json.dumps(out))
     if dist is not None:

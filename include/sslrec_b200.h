@@ -204,10 +204,11 @@ SSL_API int ssl_axpy(const float *x, float *y, int64_t n, const float *gscale, f
 
 /* ------------------------------------------------------------------------------------------
  * a20  Adam (trainer.py:45-49,68 -> torch.optim.Adam, amsgrad off): one fused pass over
- * p, g, m, v.  step is 1-based; weight_decay is folded into g as torch does.
+ * p, g, m, v.  step is 1-based; weight_decay is folded into g as torch does.  Hyper-parameters are
+ * doubles (Python floats): 1 - beta and the bias corrections are formed in double, then rounded once.
  * ------------------------------------------------------------------------------------------ */
-SSL_API int ssl_adam_step(float *p, const float *g, float *m, float *v, int64_t n, int64_t step, float lr, float beta1,
-                  float beta2, float eps, float weight_decay, void *stream);
+SSL_API int ssl_adam_step(float *p, const float *g, float *m, float *v, int64_t n, int64_t step, double lr, double beta1,
+                  double beta2, double eps, double weight_decay, void *stream);
 
 /* ------------------------------------------------------------------------------------------
  * a18  full_predict + _mask_predict (lightgcn.py:58-66, base_model.py:35-36) and the top-k that

@@ -69,7 +69,7 @@ def _load():
         'ssl_sumsq': (C.c_int, [vp, i64, vp, vp]),
         'ssl_sum': (C.c_int, [vp, i64, f32, vp, vp]),
         'ssl_axpy': (C.c_int, [vp, vp, i64, vp, f32, vp]),
-        'ssl_adam_step': (C.c_int, [vp, vp, vp, vp, i64, i64, f32, f32, f32, f32, f32, vp]),
+        'ssl_adam_step': (C.c_int, [vp, vp, vp, vp, i64, i64, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, vp]),
         'ssl_predict_mask': (C.c_int, [vp, i64, vp, i64, vp, i64, i64, i32, vp, vp, vp, vp, vp]),
         'ssl_topk': (C.c_int, [vp, i64, i64, i32, vp, vp, vp]),
     }

@@ -287,32 +287,35 @@ __global__ void axpy_kernel(const float *__restrict__ x, float *__restrict__ y, 
     }
 }
 
-__device__ __forceinline__ void adam1(float &p, float g, float &m, float &v, float b1, float b2, float step_size,
-                                      float inv_bc2_sqrt, float eps, float wd) {
+struct AdamK {
+    float b1, b2, omb1, omb2, step_size, inv_bc2_sqrt, eps, wd;   // omb = 1 - beta evaluated in double on the host, as torch does
+};
+__device__ __forceinline__ void adam1(float &p, float g, float &m, float &v, const AdamK &k) {
+    const float b1 = k.b1, b2 = k.b2, step_size = k.step_size, inv_bc2_sqrt = k.inv_bc2_sqrt, eps = k.eps, wd = k.wd;
     if (wd != 0.f) g = fmaf(wd, p, g);
-    m = fmaf(b1, m, (1.f - b1) * g);              // exp_avg.lerp_(grad, 1 - beta1)
-    v = fmaf(b2, v, (1.f - b2) * g * g);          // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+    m = fmaf(b1, m, k.omb1 * g);                  // exp_avg.lerp_(grad, 1 - beta1)
+    v = fmaf(b2, v, k.omb2 * g * g);              // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
     const float denom = sqrtf(v) * inv_bc2_sqrt + eps;
     p -= step_size * (m / denom);
 }
 __global__ void adam_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m, float *__restrict__ v,
-                            int64_t n, float b1, float b2, float step_size, float inv_bc2_sqrt, float eps, float wd) {
+                            int64_t n, AdamK k) {
     const int64_t n4 = n / 4;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
         float4 pv = *reinterpret_cast<float4 *>(p + i * 4), mv = *reinterpret_cast<float4 *>(m + i * 4),
                vv = *reinterpret_cast<float4 *>(v + i * 4);
         const float4 gv = ssl::ldg4(g + i * 4);
-        adam1(pv.x, gv.x, mv.x, vv.x, b1, b2, step_size, inv_bc2_sqrt, eps, wd);
-        adam1(pv.y, gv.y, mv.y, vv.y, b1, b2, step_size, inv_bc2_sqrt, eps, wd);
-        adam1(pv.z, gv.z, mv.z, vv.z, b1, b2, step_size, inv_bc2_sqrt, eps, wd);
-        adam1(pv.w, gv.w, mv.w, vv.w, b1, b2, step_size, inv_bc2_sqrt, eps, wd);
+        adam1(pv.x, gv.x, mv.x, vv.x, k);
+        adam1(pv.y, gv.y, mv.y, vv.y, k);
+        adam1(pv.z, gv.z, mv.z, vv.z, k);
+        adam1(pv.w, gv.w, mv.w, vv.w, k);
         *reinterpret_cast<float4 *>(p + i * 4) = pv;
         *reinterpret_cast<float4 *>(m + i * 4) = mv;
         *reinterpret_cast<float4 *>(v + i * 4) = vv;
     }
     if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
         const int64_t i = n4 * 4 + threadIdx.x;
-        adam1(p[i], g[i], m[i], v[i], b1, b2, step_size, inv_bc2_sqrt, eps, wd);
+        adam1(p[i], g[i], m[i], v[i], k);
     }
 }
 
@@ -474,18 +477,19 @@ extern "C" int ssl_axpy(const float *x, float *y, int64_t n, const float *gscale
     return SSL_OK;
 }
 
-extern "C" int ssl_adam_step(float *p, const float *g, float *m, float *v, int64_t n, int64_t step, float lr, float beta1,
-                             float beta2, float eps, float weight_decay, void *stream) {
+extern "C" int ssl_adam_step(float *p, const float *g, float *m, float *v, int64_t n, int64_t step, double lr, double beta1,
+                             double beta2, double eps, double weight_decay, void *stream) {
     SSL_CHECK_ARG(p && g && m && v && step >= 1, "ssl_adam_step: bad argument");
     SSL_CHECK_ARG(((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v)) & 15) == 0,
                   "ssl_adam_step: pointers must be 16-byte aligned");
     if (n == 0) return SSL_OK;
-    const double bc1 = 1.0 - std::pow((double)beta1, (double)step);
-    const double bc2 = 1.0 - std::pow((double)beta2, (double)step);
-    const float step_size = (float)((double)lr / bc1);
+    const double bc1 = 1.0 - std::pow(beta1, (double)step);
+    const double bc2 = 1.0 - std::pow(beta2, (double)step);
+    const float step_size = (float)(lr / bc1);
     const float inv_bc2_sqrt = (float)(1.0 / std::sqrt(bc2));
     const int blocks = (int)std::min<int64_t>(ssl::kNumSM * 8, (n / 4 + 255) / 256 + 1);
-    adam_kernel<<<blocks, 256, 0, STREAM>>>(p, g, m, v, n, beta1, beta2, step_size, inv_bc2_sqrt, eps, weight_decay);
+    const AdamK k{(float)beta1, (float)beta2, (float)(1.0 - beta1), (float)(1.0 - beta2), step_size, inv_bc2_sqrt, (float)eps, (float)weight_decay};
+    adam_kernel<<<blocks, 256, 0, STREAM>>>(p, g, m, v, n, k);
     SSL_LAUNCH_CHECK("adam_kernel");
     return SSL_OK;
 }

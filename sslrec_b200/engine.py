@@ -54,11 +54,15 @@ class KernelTimer:
     def __init__(self):
         self.records = []          # (name, meta, start_event, end_event)
 
+    def launches(self):
+        """[(name, meta, milliseconds)] -- call after a device synchronize."""
+        return [(name, meta, a.elapsed_time(b)) for name, meta, a, b in self.records]
+
     def summary(self):
         out = {}
-        for name, meta, a, b in self.records:
+        for name, meta, ms in self.launches():
             e = out.setdefault(name, dict(ms=0.0, launches=0, meta=meta))
-            e['ms'] += a.elapsed_time(b)
+            e['ms'] += ms
             e['launches'] += 1
         return out
 
@@ -272,7 +276,14 @@ class Propagation:
 
     def _launch(self, a: PropArgs, ref: torch.Tensor):
         name = 'prop_bwd' if a.transpose else 'prop_fwd'
-        with torch.cuda.device(ref.device), _timed(name, dict(views=a.n_views, in_views=a.in_views, dim=a.dim)):
+        meta = None
+        if TIMER is not None:
+            shared = a.in_views == 1 and not any(a.edge_mode[i] for i in range(a.n_views))
+            meta = dict(views=a.n_views, gather_views=1 if shared else a.n_views, dim=a.dim, residual=bool(a.residual),
+                        x_out=bool(a.x_out), sum_out=bool(a.sum_out), reduce_views=bool(a.reduce_views),
+                        sum_src=[a.sum_src_views[i] for i in range(a.n_sum_src)], reg_src=bool(a.reg_src),
+                        nnz=self.plan.nnz, rows=self.plan.n_rows)
+        with torch.cuda.device(ref.device), _timed(name, meta):
             check(lib.ssl_propagate_layer(self.plan.handle, C.byref(a), _stream(ref)), 'ssl_propagate_layer')
 
     def _node_drop(self, x: torch.Tensor, out: torch.Tensor, backward: bool):
