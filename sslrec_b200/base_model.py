@@ -5,7 +5,9 @@ from __future__ import annotations
 import torch
 from torch import nn
 
+from ._lib import check, lib
 from .config import configs
+from .graph import GraphPlan
 
 
 class BaseModel(nn.Module):
@@ -54,3 +56,41 @@ class BaseModel(nn.Module):
         if hasattr(self, 'user_embeds') and hasattr(self, 'item_embeds'):
             self._retie()
         return out
+
+    # ---- runtime shared by the drop-in models ----------------------------------------------------
+    def _init_runtime(self, data_handler):
+        from . import engine as E
+        self._seeds = E.SeedStream(configs.get('train', {}).get('seed', 2023))
+        self._plans = {}
+        self._state = None
+        self._inject = None        # tests: dict of injected masks / noise
+        self.comm = None           # parallel.RowShard for row-sharded multi-GPU runs
+
+    def _plan(self, adj=None) -> GraphPlan:
+        """CSR plan of an adjacency tensor, built once per (tensor, device)."""
+        adj = self.adj if adj is None else adj
+        dev = self.user_embeds.device
+        key = (id(adj), str(dev))
+        if key not in self._plans:
+            if dev.type != 'cuda':
+                raise RuntimeError('sslrec_b200 models run on CUDA only (move the model with .to("cuda")); there is no CPU path')
+            if self.comm is not None:
+                self._plans[key] = self.comm.make_plan(adj, dev)
+            else:
+                self._plans[key] = GraphPlan.from_torch_adj(adj, dev, need_rev=self._inject is not None)
+        return self._plans[key]
+
+    def _predict(self, user_embeds, item_embeds, batch_data):
+        """E_u[users] E_i^T with the training positives masked to -1e8 (lightgcn.py:61-65,
+        base_model.py:35-36) in one kernel; no [Bt, I] temporaries besides the result."""
+        pck_users, train_mask = batch_data
+        pck_users = pck_users.long().contiguous()
+        n_b = pck_users.shape[0]
+        preds = torch.empty(n_b, self.item_num, device=user_embeds.device, dtype=torch.float32)
+        mask = None if train_mask is None else train_mask.long().contiguous()
+        with torch.cuda.device(preds.device):
+            check(lib.ssl_predict_mask(user_embeds.data_ptr(), user_embeds.stride(0), item_embeds.data_ptr(), item_embeds.stride(0),
+                                       pck_users.data_ptr(), n_b, self.item_num, self.embedding_size,
+                                       None if mask is None else mask.data_ptr(), None, None, preds.data_ptr(),
+                                       torch.cuda.current_stream(preds.device).cuda_stream), 'ssl_predict_mask')
+        return preds

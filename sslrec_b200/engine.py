@@ -151,9 +151,14 @@ class Rows:
     where their gradient goes (a sink of the same shape, created zeroed on first use)."""
 
     def __init__(self, base: torch.Tensor, v: int, n_views: int, off: int, n: int, dim: int,
-                 sink_get=None, token: Optional[torch.Tensor] = None):
+                 sink_get=None, token: Optional[torch.Tensor] = None, comm=None):
         self.base, self.v, self.n_views, self.off, self.n, self.dim = base, v, n_views, off, n, dim
         self.sink_get, self.token = sink_get, token
+        self.comm = comm          # RowShard: as a *table* operand only the rank's own rows are contracted
+
+    def sub(self, lo: int, hi: int) -> 'Rows':
+        """The same reference restricted to global rows [lo, hi) of the underlying tensor."""
+        return Rows(self.base, self.v, self.n_views, lo, hi - lo, self.dim, self.sink_get, self.token)
 
     @property
     def stride(self) -> int:
@@ -214,12 +219,13 @@ class PropState:
 
     # ---- row references ------------------------------------------------------------------------
     def _rows(self, which, v: int, off: int, n: int) -> Rows:
+        comm = self.prop.comm
         if which == 'sum':
-            return Rows(self.E, v, self.n_views, off, n, self.dim, self.g_sum, self.token)
+            return Rows(self.E, v, self.n_views, off, n, self.dim, self.g_sum, self.token, comm)
         k = int(which)
         if k == 0:           # layer 0 is E0 itself (ncl.py:75)
-            return Rows(self.e0, 0, 1, off, n, self.dim, self.g_e0, self.token)
-        return Rows(self.layers[k], v, self.n_views, off, n, self.dim, lambda: self.g_layer(k), self.token)
+            return Rows(self.e0, 0, 1, off, n, self.dim, self.g_e0, self.token, comm)
+        return Rows(self.layers[k], v, self.n_views, off, n, self.dim, lambda: self.g_layer(k), self.token, comm)
 
     def users(self, v: int = 0, which='sum') -> Rows:
         return self._rows(which, v, 0, self.n_user)
@@ -310,6 +316,7 @@ class Propagation:
         N, d, V = e0.shape[0], e0.shape[1], len(self.views)
         r0, nl = self.plan.row_offset, self.plan.n_rows
         opts = dict(device=e0.device, dtype=torch.float32)
+        nalloc = nl if self.comm is None else self.comm.block
         if self.any_node:
             x0 = torch.empty(N, V, d, **opts)
             self._node_drop(e0, x0, backward=False)
@@ -325,10 +332,10 @@ class Propagation:
             a.in_views = in_views
             a.x_in = x_prev.data_ptr()
             need_out = (k < self.n_layers) or (k in self.keep_layers)
-            x_out = torch.empty(nl, V, d, **opts) if need_out else None
+            x_out = torch.empty(nalloc, V, d, **opts) if need_out else None
             a.x_out = _ptr(x_out)
             if k == self.sum_layers:
-                E_loc = torch.empty(nl, V, d, **opts)
+                E_loc = torch.empty(nalloc, V, d, **opts)
                 a.sum_out = E_loc.data_ptr()
                 a.n_sum_src = len(srcs)
                 for i, (s, sv) in enumerate(srcs):
@@ -355,6 +362,7 @@ class Propagation:
         N, d, V = st.n, st.dim, st.n_views
         r0, nl = self.plan.row_offset, self.plan.n_rows
         opts = dict(device=e0.device, dtype=torch.float32)
+        nalloc = nl if self.comm is None else self.comm.block
         L, S = self.n_layers, self.sum_layers
 
         def residual(k: int) -> Optional[torch.Tensor]:
@@ -381,6 +389,10 @@ class Propagation:
                 out = out + g_e0
             return out
         D = residual(top)
+        if self.comm is not None:
+            # dense table gradients exist only for the rank's own rows (the batch-row scatters are
+            # replicated): exchange the owned blocks so every rank reads the complete D_top
+            D = self._gather(self._own_block(D))
         for k in range(top, 0, -1):           # D_{k-1} = A_v^T D_k + residual(k-1)
             a = self._args(d, k, transpose=True)
             a.in_views = V
@@ -390,13 +402,13 @@ class Propagation:
                 a.residual = res.data_ptr() + 4 * (r0 * V * d)
             last = (k == 1)
             if last and not self.any_node:
-                out = torch.empty(nl, d, **opts)
+                out = torch.empty(nalloc, d, **opts)
                 a.sum_out, a.reduce_views = out.data_ptr(), 1
                 if g_e0 is not None:
                     a.reg_src, a.reg_coef = g_e0.data_ptr() + 4 * (r0 * d), 1.0
                 self._launch(a, e0)
                 return self._gather_2d(out)
-            x_out = torch.empty(nl, V, d, **opts)
+            x_out = torch.empty(nalloc, V, d, **opts)
             a.x_out = x_out.data_ptr()
             self._launch(a, e0)
             D = self._gather(x_out)
@@ -406,6 +418,13 @@ class Propagation:
         out = g_e0.clone() if g_e0 is not None else torch.zeros_like(e0)
         self._node_drop(d0, out, backward=True)
         return out
+
+    def _own_block(self, full: torch.Tensor) -> torch.Tensor:
+        c = self.comm
+        blk = torch.zeros((c.block,) + tuple(full.shape[1:]), device=full.device, dtype=full.dtype) if c.n_local < c.block \
+            else torch.empty((c.block,) + tuple(full.shape[1:]), device=full.device, dtype=full.dtype)
+        blk[:c.n_local].copy_(full[c.r0:c.r1])
+        return blk
 
     def _gather_2d(self, local: torch.Tensor) -> torch.Tensor:
         if self.comm is None:
@@ -444,6 +463,38 @@ def propagate(prop: Propagation, user_e: torch.Tensor, item_e: torch.Tensor, e0:
         st.token = token
         return st
     return prop.forward(e0.detach(), user_e.shape[0])
+
+
+class _SpmmFn(torch.autograd.Function):
+    """Single masked propagation layer on a dense autograd tensor: Y = A_m X, dX = A_m^T dY (the same
+    kernel with transpose = 1).  Used where layers are interleaved with other autograd ops (HCCF)."""
+
+    @staticmethod
+    def forward(ctx, x, plan, view, layer):
+        ctx.pack = (plan, view, layer)
+        return _spmm_once(plan, x.detach(), view, layer, False)
+
+    @staticmethod
+    def backward(ctx, g):
+        plan, view, layer = ctx.pack
+        return _spmm_once(plan, g, view, layer, True), None, None, None
+
+
+def _spmm_once(plan: GraphPlan, x: torch.Tensor, view: ViewSpec, layer: int, transpose: bool) -> torch.Tensor:
+    _require_cuda(x, 'spmm input')
+    x = x.contiguous()
+    prop = Propagation(plan, [view], max(1, layer))
+    a = prop._args(x.shape[1], layer, transpose)
+    out = torch.empty(plan.n_rows, 1, x.shape[1], device=x.device, dtype=torch.float32)
+    a.in_views, a.x_in, a.x_out = 1, x.data_ptr(), out.data_ptr()
+    a.noise_mode[0] = 0
+    prop._launch(a, x)
+    return out.view(plan.n_rows, x.shape[1])
+
+
+def spmm(plan: GraphPlan, x: torch.Tensor, view: Optional[ViewSpec] = None, layer: int = 1) -> torch.Tensor:
+    """t.spmm(adj, embeds) (lightgcn.py:29 / hccf.py:36) with an optional in-kernel edge mask."""
+    return _SpmmFn.apply(x, plan, view if view is not None else ViewSpec(), layer)
 
 
 def flat_table(user_e: torch.Tensor, item_e: torch.Tensor) -> torch.Tensor:
@@ -541,9 +592,15 @@ def _nce_fwd(e1: Rows, e2: Rows, table: Rows, idx, idx2, tau, norm_mode, mean, d
     f = dict(device=dev, dtype=torch.float32)
     a_hat, a_t, rinv1 = torch.empty(Bp, d, **f), torch.empty(Bp // 64, d, 64, **f), torch.empty(B, **f)
     p_hat, rinv2 = torch.empty(Bp, d, **f), torch.empty(B, **f)
-    t_hat, t_t, rinv_t = torch.empty(npad, d, **f), torch.empty(npad // 64, d, 64, **f), torch.empty(n, **f)
+    comm = table.comm
+    if comm is not None:                  # contract only this rank's rows of the table; partials are all-reduced
+        lo, hi = comm.local_range(table.off, table.n)
+        table = table.sub(lo, hi)
+        n = table.n
+        npad = max(64, ceil_to(n, 64))
+    t_hat, t_t, rinv_t = torch.empty(npad, d, **f), torch.empty(npad // 64, d, 64, **f), torch.empty(max(n, 1), **f)
     n_split = choose_split((B + 127) // 128, npad // 64)
-    rs_part, o_part = torch.empty(n_split, B, **f), torch.empty(n_split, B, d, **f)
+    rs_part, o_part = torch.zeros(n_split, B, **f), torch.zeros(n_split, B, d, **f)
     rowsum, obar, loss_b, out = torch.empty(B, **f), torch.empty(B, d, **f), torch.empty(B, **f), torch.empty((), **f)
     off = LOG2E / tau
     with torch.cuda.device(dev):
@@ -557,6 +614,10 @@ def _nce_fwd(e1: Rows, e2: Rows, table: Rows, idx, idx2, tau, norm_mode, mean, d
         with _timed('nce_gemm_fwd', dict(B=B, n=n, dim=d)):
             check(lib.ssl_softmax_gemm(a_hat.data_ptr(), B, t_hat.data_ptr(), t_t.data_ptr(), n, d, None, off, n_split,
                                        rs_part.data_ptr(), o_part.data_ptr(), s), 'ssl_softmax_gemm(fwd)')
+        if comm is not None:
+            red = torch.cat([o_part.sum(0), rs_part.sum(0).unsqueeze(1)], 1)         # [B, d+1]
+            comm.allreduce_sum(red)
+            o_part, rs_part, n_split = red[:, :d].contiguous().unsqueeze(0), red[:, d].contiguous().unsqueeze(0), 1
         check(lib.ssl_nce_finalize(rs_part.data_ptr(), o_part.data_ptr(), n_split, B, d, a_hat.data_ptr(), p_hat.data_ptr(),
                                    tau, deno_eps * math.exp(-1.0 / tau), rowsum.data_ptr(), obar.data_ptr(),
                                    loss_b.data_ptr(), s), 'ssl_nce_finalize')
@@ -579,7 +640,7 @@ def _nce_bwd(saved, g):
             check(lib.ssl_nce_bwd_rows(a_hat.data_ptr(), p_hat.data_ptr(), obar.data_ptr(), rinv1.data_ptr(), rinv2.data_ptr(),
                                        idx.data_ptr(), B, d, tau, g.data_ptr(), scale, g1, e1.stride, g2, e2.stride, s),
                   'ssl_nce_bwd_rows')
-        if gt is not None:
+        if gt is not None and n > 0:
             colscale = torch.empty(ceil_to(B, 64), **f)
             check(lib.ssl_nce_colscale(rowsum.data_ptr(), B, g.data_ptr(), scale, colscale.data_ptr(), s), 'ssl_nce_colscale')
             n_split = choose_split((n + 127) // 128, ceil_to(B, 64) // 64)

@@ -2,16 +2,12 @@
 full_predict, ``is_training`` / ``final_embeds`` cache semantics are the reference's)."""
 from __future__ import annotations
 
-import ctypes as C
-
 import torch
 
 from .. import engine as E
-from .._lib import check, lib
 from ..aug_utils import EdgeDrop
 from ..base_model import BaseModel
 from ..config import configs
-from ..graph import GraphPlan
 from ..loss_utils import cal_bpr_loss, reg_params
 
 
@@ -31,26 +27,7 @@ class LightGCN(BaseModel):
         self.is_training = True
         self.final_embeds = None
 
-        self._seeds = E.SeedStream(configs.get('train', {}).get('seed', 2023))
-        self._plans = {}
-        self._state = None
-        self._inject = None        # tests: dict of injected masks / noise (see tests/)
-        self.comm = None           # row-sharded multi-GPU communicator (parallel.RowShard), optional
-
-    # ---- adjacency plan (built once per adjacency tensor and device) ---------------------------
-    def _plan(self, adj=None) -> GraphPlan:
-        adj = self.adj if adj is None else adj
-        dev = self.user_embeds.device
-        key = (id(adj), str(dev))
-        if key not in self._plans:
-            if dev.type != 'cuda':
-                raise RuntimeError('sslrec_b200 models run on CUDA only (move the model with .to("cuda"))')
-            need_rev = self._inject is not None
-            if self.comm is not None:
-                self._plans[key] = self.comm.make_plan(adj, dev)
-            else:
-                self._plans[key] = GraphPlan.from_torch_adj(adj, dev, need_rev=need_rev)
-        return self._plans[key]
+        self._init_runtime(data_handler)
 
     def _table(self) -> torch.Tensor:
         return E.flat_table(self.user_embeds, self.item_embeds)
@@ -87,23 +64,6 @@ class LightGCN(BaseModel):
         loss = bpr_loss + reg_loss
         losses = {'bpr_loss': bpr_loss, 'reg_loss': reg_loss}
         return loss, losses
-
-    def _predict(self, user_embeds, item_embeds, batch_data):
-        """E_u[users] E_i^T with the training positives masked to -1e8 (lightgcn.py:61-65,
-        base_model.py:35-36), one kernel, no [Bt, I] temporaries besides the result."""
-        pck_users, train_mask = batch_data
-        pck_users = pck_users.long().contiguous()
-        n_b = pck_users.shape[0]
-        preds = torch.empty(n_b, self.item_num, device=user_embeds.device, dtype=torch.float32)
-        mask = None
-        if train_mask is not None:
-            mask = train_mask.long().contiguous()
-        with torch.cuda.device(preds.device):
-            check(lib.ssl_predict_mask(user_embeds.data_ptr(), user_embeds.stride(0), item_embeds.data_ptr(), item_embeds.stride(0),
-                                       pck_users.data_ptr(), n_b, self.item_num, self.embedding_size,
-                                       None if mask is None else mask.data_ptr(), None, None, preds.data_ptr(),
-                                       torch.cuda.current_stream(preds.device).cuda_stream), 'ssl_predict_mask')
-        return preds
 
     def full_predict(self, batch_data):
         user_embeds, item_embeds = self.forward(self.adj, 1.0)

@@ -12,7 +12,7 @@ import ssl_test_helpers as H
 
 pytestmark = pytest.mark.gpu
 
-CASES = [('lightgcn', 'tiny'), ('simgcl', 'tiny'), ('sgl', 'tiny'), ('sgl_nd', 'tiny'), ('ncl', 'tiny'),
+CASES = [('lightgcn', 'tiny'), ('simgcl', 'tiny'), ('sgl', 'tiny'), ('sgl_nd', 'tiny'), ('ncl', 'tiny'), ('hccf', 'tiny'),
          ('lightgcn', 'small'), ('simgcl', 'small'), ('sgl', 'small'), ('simgcl', 'mid')]
 
 
@@ -23,7 +23,10 @@ def _run(model_key, case_name):
     adj = O.normalized_adjacency(case['rows'], case['cols'], case['n_user'], case['n_item'])
     dr = replay.draws(model_key, case, hp, adj)
     model, dh = H.make_model(model_key, case, hp, inject=H.gpu_injection(model_key, case, hp, adj, dr))
-    model.load_state_dict({'user_embeds': case['user_e'], 'item_embeds': case['item_e']})
+    sd = {'user_embeds': case['user_e'], 'item_embeds': case['item_e']}
+    if 'user_w' in dr:
+        sd['user_hyper_embeds'], sd['item_hyper_embeds'] = dr['user_w'], dr['item_w']
+    model.load_state_dict(sd)
     if model_key == 'ncl':
         model.user_centroids = torch.from_numpy(g['user_centroids']).cuda()
         model.item_centroids = torch.from_numpy(g['item_centroids']).cuda()

@@ -1,0 +1,90 @@
+"""N > 1: the row-shard plumbing on CPU (gloo, world_size 2) and, when two GPUs are visible, the
+sharded training step against the single-GPU one."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _gloo_worker(rank, world, port, n):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from sslrec_b200.parallel import RowShard
+    sh = RowShard(dist, rank, world, n)
+    full = torch.arange(n * 2 * 3, dtype=torch.float32).view(n, 2, 3)
+    local = torch.zeros(sh.block, 2, 3)
+    local[:sh.n_local] = full[sh.r0:sh.r1]
+    got = sh.allgather_rows(local)
+    assert torch.equal(got, full)
+    # every global row belongs to exactly one rank; side ranges split without gaps
+    owned = torch.zeros(n)
+    owned[sh.r0:sh.r1] = 1
+    dist.all_reduce(owned)
+    assert torch.equal(owned, torch.ones(n))
+    n_user = n // 3
+    lo_u, hi_u = sh.local_range(0, n_user)
+    lo_i, hi_i = sh.local_range(n_user, n - n_user)
+    cnt = torch.tensor([hi_u - lo_u, hi_i - lo_i], dtype=torch.float32)
+    dist.all_reduce(cnt)
+    assert cnt.tolist() == [n_user, n - n_user]
+    # partial (row sum, weighted sum) of a sharded softmax contraction all-reduce to the full one
+    g = torch.Generator().manual_seed(0)
+    a, t = torch.randn(5, 4, generator=g), torch.randn(n, 4, generator=g)
+    e = torch.exp(a @ t[sh.r0:sh.r1].T)
+    red = torch.cat([e @ t[sh.r0:sh.r1], e.sum(1, keepdim=True)], 1)
+    sh.allreduce_sum(red)
+    ef = torch.exp(a @ t.T)
+    assert torch.allclose(red[:, :4], ef @ t, rtol=1e-5) and torch.allclose(red[:, 4], ef.sum(1), rtol=1e-5)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('n', [10, 11, 64])
+def test_row_shard_plumbing_gloo_world2(n):
+    mp.spawn(_gloo_worker, args=(2, _free_port(), n), nprocs=2, join=True)
+
+
+def _gpu_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests'))
+    import ssl_test_helpers as H
+    from oracle import inputs, replay
+    from sslrec_b200.parallel import RowShard
+    g = replay.load_golden('simgcl', 'small')
+    case = inputs.make_case('small')
+    res = {}
+    for sharded in (False, True):
+        model, _ = H.make_model('simgcl', case, g['hp'], device=f'cuda:{rank}')
+        model.load_state_dict({'user_embeds': case['user_e'], 'item_embeds': case['item_e']})
+        if sharded:
+            model.comm = RowShard(dist, rank, world, case['n_user'] + case['n_item'])
+            model._plans.clear()
+        batch = [torch.from_numpy(case[k]).cuda() for k in ('ancs', 'poss', 'negs')]
+        loss, _ = model.cal_loss(batch)
+        loss.backward()
+        res[sharded] = (loss.item(), model.user_embeds.grad.clone(), model.item_embeds.grad.clone())
+    assert abs(res[True][0] - res[False][0]) <= 1e-6 * max(1.0, abs(res[False][0]))
+    for a, b in zip(res[True][1:], res[False][1:]):
+        assert torch.allclose(a, b, rtol=1e-4, atol=1e-7 + 1e-5 * b.abs().max().item())
+    dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_sharded_step_matches_single_gpu():
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs (run with gpurun --gpus 2)')
+    mp.spawn(_gpu_worker, args=(2, _free_port(), None), nprocs=2, join=True)
