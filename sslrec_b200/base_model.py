@@ -74,7 +74,7 @@ class BaseModel(nn.Module):
         if key not in self._plans:
             if dev.type != 'cuda':
                 raise RuntimeError('sslrec_b200 models run on CUDA only (move the model with .to("cuda")); there is no CPU path')
-            if self.comm is not None:
+            if self.comm is not None and self.comm.shard_propagation:
                 self._plans[key] = self.comm.make_plan(adj, dev)
             else:
                 self._plans[key] = GraphPlan.from_torch_adj(adj, dev, need_rev=self._inject is not None)

@@ -219,7 +219,7 @@ class PropState:
 
     # ---- row references ------------------------------------------------------------------------
     def _rows(self, which, v: int, off: int, n: int) -> Rows:
-        comm = self.prop.comm
+        comm = self.prop.loss_comm
         if which == 'sum':
             return Rows(self.E, v, self.n_views, off, n, self.dim, self.g_sum, self.token, comm)
         k = int(which)
@@ -246,13 +246,14 @@ class Propagation:
     """
 
     def __init__(self, plan: GraphPlan, views: Sequence[ViewSpec], n_layers: int, sum_layers: Optional[int] = None,
-                 keep_layers: Sequence[int] = (), noise_eps: float = 0.0, comm=None):
+                 keep_layers: Sequence[int] = (), noise_eps: float = 0.0, comm=None, loss_comm=None):
         self.plan, self.views = plan, list(views)
         self.n_layers = int(n_layers)
         self.sum_layers = self.n_layers if sum_layers is None else int(sum_layers)
         self.keep_layers = set(int(k) for k in keep_layers)
         self.noise_eps = float(noise_eps)
-        self.comm = comm       # row-sharded multi-GPU: object with .allgather_rows(local [n_loc, V, d]) -> full
+        self.comm = comm       # row-sharded propagation: object with .allgather_rows(local [block, V, d]) -> full
+        self.loss_comm = loss_comm if loss_comm is not None else comm    # shards the InfoNCE table rows
         if not 1 <= len(self.views) <= _lib.MAX_VIEWS:
             raise ValueError('1..%d views' % _lib.MAX_VIEWS)
         if self.sum_layers > self.n_layers or self.sum_layers + 1 > _lib.MAX_SUM_SRC + 1:
@@ -389,10 +390,6 @@ class Propagation:
                 out = out + g_e0
             return out
         D = residual(top)
-        if self.comm is not None:
-            # dense table gradients exist only for the rank's own rows (the batch-row scatters are
-            # replicated): exchange the owned blocks so every rank reads the complete D_top
-            D = self._gather(self._own_block(D))
         for k in range(top, 0, -1):           # D_{k-1} = A_v^T D_k + residual(k-1)
             a = self._args(d, k, transpose=True)
             a.in_views = V
@@ -593,8 +590,9 @@ def _nce_fwd(e1: Rows, e2: Rows, table: Rows, idx, idx2, tau, norm_mode, mean, d
     a_hat, a_t, rinv1 = torch.empty(Bp, d, **f), torch.empty(Bp // 64, d, 64, **f), torch.empty(B, **f)
     p_hat, rinv2 = torch.empty(Bp, d, **f), torch.empty(B, **f)
     comm = table.comm
+    full_table = table
     if comm is not None:                  # contract only this rank's rows of the table; partials are all-reduced
-        lo, hi = comm.local_range(table.off, table.n)
+        lo, hi = comm.side_range(table.off, table.n)
         table = table.sub(lo, hi)
         n = table.n
         npad = max(64, ceil_to(n, 64))
@@ -622,12 +620,12 @@ def _nce_fwd(e1: Rows, e2: Rows, table: Rows, idx, idx2, tau, norm_mode, mean, d
                                    tau, deno_eps * math.exp(-1.0 / tau), rowsum.data_ptr(), obar.data_ptr(),
                                    loss_b.data_ptr(), s), 'ssl_nce_finalize')
         check(lib.ssl_sum(loss_b.data_ptr(), B, (1.0 / B) if mean else 1.0, out.data_ptr(), s), 'ssl_sum')
-    saved = (e1, e2, table, idx, tau, mean, a_hat, a_t, p_hat, rinv1, rinv2, t_hat, rinv_t, rowsum, obar)
+    saved = (e1, e2, table, idx, tau, mean, a_hat, a_t, p_hat, rinv1, rinv2, t_hat, rinv_t, rowsum, obar, full_table, comm)
     return out, saved
 
 
 def _nce_bwd(saved, g):
-    (e1, e2, table, idx, tau, mean, a_hat, a_t, p_hat, rinv1, rinv2, t_hat, rinv_t, rowsum, obar) = saved
+    (e1, e2, table, idx, tau, mean, a_hat, a_t, p_hat, rinv1, rinv2, t_hat, rinv_t, rowsum, obar, full_table, comm) = saved
     dev, d = g.device, table.dim
     B, n = idx.numel(), table.n
     g = g.contiguous()
@@ -636,6 +634,11 @@ def _nce_bwd(saved, g):
     with torch.cuda.device(dev):
         s = _stream(g)
         g1, g2, gt = e1.grad_ptr(), e2.grad_ptr(), table.grad_ptr()
+        gt_stride, local_dt = table.stride, None
+        if comm is not None and gt is not None:
+            # own rows' dense gradient goes to a compact block that is all-gathered and added to the sink
+            local_dt = torch.zeros(comm.side_block(full_table.n), d, **f)
+            gt, gt_stride = local_dt.data_ptr(), d
         if g1 is not None or g2 is not None:
             check(lib.ssl_nce_bwd_rows(a_hat.data_ptr(), p_hat.data_ptr(), obar.data_ptr(), rinv1.data_ptr(), rinv2.data_ptr(),
                                        idx.data_ptr(), B, d, tau, g.data_ptr(), scale, g1, e1.stride, g2, e2.stride, s),
@@ -649,7 +652,11 @@ def _nce_bwd(saved, g):
                 check(lib.ssl_softmax_gemm(t_hat.data_ptr(), n, a_hat.data_ptr(), a_t.data_ptr(), B, d, colscale.data_ptr(),
                                            LOG2E / tau, n_split, None, dt_part.data_ptr(), s), 'ssl_softmax_gemm(bwd)')
             check(lib.ssl_nce_bwd_table(dt_part.data_ptr(), n_split, t_hat.data_ptr(), rinv_t.data_ptr(), n, d, gt,
-                                        table.stride, 1, s), 'ssl_nce_bwd_table')
+                                        gt_stride, 1, s), 'ssl_nce_bwd_table')
+        if local_dt is not None:
+            dense = comm.allgather_side(local_dt, full_table.n)
+            sink = full_table.sink_get().view(-1, full_table.n_views, d)
+            sink[full_table.off:full_table.off + full_table.n, full_table.v, :] += dense
 
 
 class _InfoNceFn(torch.autograd.Function):

@@ -35,8 +35,9 @@ class LightGCN(BaseModel):
     def _propagate(self, views, n_layers=None, sum_layers=None, keep_layers=(), noise_eps=0.0, adj=None) -> E.PropState:
         """All augmented views, all layers and the layer sum: replaces the loop of t.spmm calls
         (lightgcn.py:28-29,38-41)."""
+        shard = self.comm is not None and self.comm.shard_propagation
         prop = E.Propagation(self._plan(adj), views, self.layer_num if n_layers is None else n_layers,
-                             sum_layers, keep_layers, noise_eps, comm=self.comm)
+                             sum_layers, keep_layers, noise_eps, comm=self.comm if shard else None, loss_comm=self.comm)
         st = E.propagate(prop, self.user_embeds, self.item_embeds, self._table())
         self._state = st
         return st

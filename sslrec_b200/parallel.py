@@ -6,8 +6,11 @@ Exchange steps -- the only collectives on the path:
   * one all-gather of the [N/world, V, d] layer output per propagation layer, forward and backward
     (each rank computes its rows from the full previous layer);
   * per InfoNCE term one all-reduce of the per-anchor partial (row sum, weighted table average)
-    [B, d+1], because the table rows (negatives) are sharded and the anchors are replicated;
+    [B, d+1], because the table rows (negatives) are sharded and the anchors are replicated, and in the
+    backward one all-gather of the [N_side/world, d] dense table-gradient blocks;
   * one all-gather of the [N/world, d] gradient block before the (replicated) Adam step.
+The propagation all-gathers only happen when the propagation itself is sharded (``shard_propagation``:
+automatic by table size); small graphs replicate the sub-millisecond SpMM and shard only the loss.
 Blocks are equal-sized (ceil(N / world), the last one padded) so the gathered buffer's first N rows
 ARE the full tensor -- no compaction copy.  Everything else (BPR on the replicated batch, the
 regulariser, Adam on the replicated table) is rank-local and bit-identical across ranks.
@@ -20,11 +23,18 @@ from .graph import GraphPlan
 
 
 class RowShard:
-    def __init__(self, dist, rank: int, world: int, n: int):
+    def __init__(self, dist, rank: int, world: int, n: int, shard_propagation='auto', dim: int = 64, views: int = 3):
         self.dist, self.rank, self.world, self.n = dist, rank, world, n
         self.block = (n + world - 1) // world
         self.r0 = min(n, rank * self.block)
         self.r1 = min(n, self.r0 + self.block)
+        # Row-sharding the propagation costs one all-gather of the whole [N, V, d] layer per layer and
+        # direction; it pays when the SpMM is long (HBM-bound tables far beyond L2, BASELINE.json config 4),
+        # not when a layer takes ~0.2 ms (the bundled datasets).  The contraction of the contrastive loss
+        # is sharded over the table rows in either mode.
+        if shard_propagation == 'auto':
+            shard_propagation = n * views * dim * 4 >= (1 << 30)
+        self.shard_propagation = bool(shard_propagation)
 
     @property
     def n_local(self) -> int:
@@ -50,7 +60,17 @@ class RowShard:
         self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
         return t
 
-    def local_range(self, off: int, n: int):
-        """Intersection of the global rows [off, off+n) with this rank's block, as (lo, hi)."""
-        lo, hi = max(off, self.r0), min(off + n, self.r1)
-        return (lo, max(lo, hi))
+    def side_block(self, n: int) -> int:
+        return (n + self.world - 1) // self.world
+
+    def side_range(self, off: int, n: int):
+        """This rank's share of the table rows [off, off+n) of one side (equal blocks, last padded)."""
+        blk = self.side_block(n)
+        lo = min(off + n, off + self.rank * blk)
+        return lo, min(off + n, lo + blk)
+
+    def allgather_side(self, local: torch.Tensor, n: int) -> torch.Tensor:
+        """local [side_block(n), d] -> [n, d] (rows of all ranks' side blocks in order)."""
+        out = torch.empty((self.world * local.shape[0],) + tuple(local.shape[1:]), device=local.device, dtype=local.dtype)
+        self.dist.all_gather_into_tensor(out, local.contiguous())
+        return out[:n]

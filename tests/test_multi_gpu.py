@@ -34,16 +34,20 @@ def _gloo_worker(rank, world, port, n):
     dist.all_reduce(owned)
     assert torch.equal(owned, torch.ones(n))
     n_user = n // 3
-    lo_u, hi_u = sh.local_range(0, n_user)
-    lo_i, hi_i = sh.local_range(n_user, n - n_user)
+    lo_u, hi_u = sh.side_range(0, n_user)
+    lo_i, hi_i = sh.side_range(n_user, n - n_user)
     cnt = torch.tensor([hi_u - lo_u, hi_i - lo_i], dtype=torch.float32)
     dist.all_reduce(cnt)
     assert cnt.tolist() == [n_user, n - n_user]
     # partial (row sum, weighted sum) of a sharded softmax contraction all-reduce to the full one
     g = torch.Generator().manual_seed(0)
     a, t = torch.randn(5, 4, generator=g), torch.randn(n, 4, generator=g)
-    e = torch.exp(a @ t[sh.r0:sh.r1].T)
-    red = torch.cat([e @ t[sh.r0:sh.r1], e.sum(1, keepdim=True)], 1)
+    lo, hi = sh.side_range(0, n)
+    e = torch.exp(a @ t[lo:hi].T)
+    red = torch.cat([e @ t[lo:hi], e.sum(1, keepdim=True)], 1)
+    blk = torch.zeros(sh.side_block(n), 4)
+    blk[:hi - lo] = t[lo:hi]
+    assert torch.equal(sh.allgather_side(blk, n), t)
     sh.allreduce_sum(red)
     ef = torch.exp(a @ t.T)
     assert torch.allclose(red[:, :4], ef @ t, rtol=1e-5) and torch.allclose(red[:, 4], ef.sum(1), rtol=1e-5)
@@ -67,19 +71,20 @@ def _gpu_worker(rank, world, port, out):
     g = replay.load_golden('simgcl', 'small')
     case = inputs.make_case('small')
     res = {}
-    for sharded in (False, True):
+    for sharded in (False, 'loss', 'all'):
         model, _ = H.make_model('simgcl', case, g['hp'], device=f'cuda:{rank}')
         model.load_state_dict({'user_embeds': case['user_e'], 'item_embeds': case['item_e']})
         if sharded:
-            model.comm = RowShard(dist, rank, world, case['n_user'] + case['n_item'])
+            model.comm = RowShard(dist, rank, world, case['n_user'] + case['n_item'], shard_propagation=(sharded == 'all'))
             model._plans.clear()
         batch = [torch.from_numpy(case[k]).cuda() for k in ('ancs', 'poss', 'negs')]
         loss, _ = model.cal_loss(batch)
         loss.backward()
         res[sharded] = (loss.item(), model.user_embeds.grad.clone(), model.item_embeds.grad.clone())
-    assert abs(res[True][0] - res[False][0]) <= 1e-6 * max(1.0, abs(res[False][0]))
-    for a, b in zip(res[True][1:], res[False][1:]):
-        assert torch.allclose(a, b, rtol=1e-4, atol=1e-7 + 1e-5 * b.abs().max().item())
+    for mode in ('loss', 'all'):
+        assert abs(res[mode][0] - res[False][0]) <= 1e-6 * max(1.0, abs(res[False][0])), mode
+        for a, b in zip(res[mode][1:], res[False][1:]):
+            assert torch.allclose(a, b, rtol=1e-4, atol=1e-7 + 1e-5 * b.abs().max().item()), mode
     dist.destroy_process_group()
 
 
