@@ -75,7 +75,8 @@ __global__ void bpr_bwd_kernel(const float *users, int64_t us, const float *item
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) rows_normalize_kernel(const float *__restrict__ x, int64_t stride, const int64_t *__restrict__ idx,
                                                            int64_t n, int dim, int mode, float alpha, float *__restrict__ out,
-                                                           float *__restrict__ out_t, float *__restrict__ rinv) {
+                                                           float *__restrict__ out_t, float *__restrict__ rinv,
+                                                           float *__restrict__ out_hi, float *__restrict__ out_lo) {
     extern __shared__ float tile[];   // [64][dim + 1]
     const int pitch = dim + 1;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -105,6 +106,11 @@ __global__ void __launch_bounds__(256) rows_normalize_kernel(const float *__rest
                 const float y = v[i] * ri * alpha;
                 tile[lr * pitch + k] = y;
                 out[row * dim + k] = y;            // rows n .. ceil64(n) are written as zeros
+                if (out_hi != nullptr) {           // tf32 split for the tensor-core contraction
+                    const float hi = __uint_as_float(__float_as_uint(y) & 0xffffe000u);
+                    out_hi[row * dim + k] = hi;
+                    out_lo[row * dim + k] = y - hi;
+                }
             }
         }
     }
@@ -384,13 +390,14 @@ extern "C" int ssl_bpr_bwd(const float *users, int64_t u_stride, const float *it
 }
 
 extern "C" int ssl_rows_normalize(const float *x, int64_t stride, const int64_t *idx, int64_t n, int32_t dim, int32_t norm_mode,
-                                  float alpha, float *out, float *out_t, float *rinv, void *stream) {
+                                  float alpha, float *out, float *out_t, float *rinv, float *out_hi, float *out_lo, void *stream) {
     SSL_CHECK_ARG(x && out, "ssl_rows_normalize: null argument");
+    SSL_CHECK_ARG((out_hi == nullptr) == (out_lo == nullptr), "ssl_rows_normalize: out_hi and out_lo go together");
     SSL_CHECK_ARG(dim >= 4 && dim <= SSL_MAX_DIM && dim % 4 == 0, "ssl_rows_normalize: dim %d must be a multiple of 4 <= %d", dim, SSL_MAX_DIM);
     SSL_CHECK_ARG(norm_mode == 0 || norm_mode == 1, "ssl_rows_normalize: bad norm_mode");
     if (n == 0) return SSL_OK;
     const size_t smem = sizeof(float) * 64 * (dim + 1);
-    rows_normalize_kernel<<<(unsigned)((n + 63) / 64), 256, smem, STREAM>>>(x, stride, idx, n, dim, norm_mode, alpha, out, out_t, rinv);
+    rows_normalize_kernel<<<(unsigned)((n + 63) / 64), 256, smem, STREAM>>>(x, stride, idx, n, dim, norm_mode, alpha, out, out_t, rinv, out_hi, out_lo);
     SSL_LAUNCH_CHECK("rows_normalize_kernel");
     return SSL_OK;
 }

@@ -1,0 +1,390 @@
+// ssl_softmax_gemm_tf32x3: the InfoNCE contraction on the 5th-generation tensor cores (tcgen05,
+// kind::tf32) with fp32-grade accuracy through 3xTF32 error compensation.
+//
+//   S  = R C^T   = R_hi C_hi^T + R_lo C_hi^T + R_hi C_lo^T          (x = x_hi + x_lo, x_hi = tf32(x))
+//   E  = exp2(S - offset) * colscale ;  rowsum += sum_c E
+//   O += E C     = E_hi C_hi   + E_lo C_hi   + E_hi C_lo
+//
+// Same contract as ssl_softmax_gemm (nce_gemm.cu): one launch is the forward of an InfoNCE term or,
+// with the operand roles swapped, its backward.  The dropped lo*lo products and the tf32 truncation
+// of the lo parts are O(2^-21) relative -- the fp32 rounding level of the FFMA kernel.
+//
+// Structure (one CTA per SM, 256 threads, warp-specialised, all synchronisation by mbarriers):
+//   warp 0 / lane 0 : TMA producer.  2-D tensor maps (SWIZZLE_128B, 32-float boxes) over the
+//                     row-major hi / lo operand arrays; the resident 128-row R tile once, the 64-row
+//                     C tiles through a 4-stage ring.
+//   warp 1 / lane 0 : MMA issuer.  GEMM1 (M=128, N=64, K=d): both operands K-major in shared memory
+//                     -> S in TMEM.  GEMM2 (M=128, N=d, K=64): A = E read from TENSOR MEMORY, B = the
+//                     SAME C tile addressed MN-major -> O in TMEM, accumulated over all tiles.
+//                     Issue order MMA1(t), MMA2(t-1): the tensor pipe works on tile t while the
+//                     epilogue warps process tile t-1.
+//   warps 4-7       : epilogue, thread = TMEM lane = row.  tcgen05.ld S, ex2, row sums in registers
+//                     (no cross-thread reduction), split E into hi / lo, tcgen05.st them back into
+//                     TMEM (E_hi over S in place); finally O is read out of TMEM once per CTA.
+//   TMEM columns    : [0,128) S/E_hi x2 buffers, [128,256) E_lo x2 buffers, [256,256+d) O.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int BM = 128, BN = 64, STAGES = 4;
+constexpr int kNumThreads = 256;
+constexpr uint32_t kTmemCols = 512;
+constexpr uint32_t COL_SE = 0, COL_ELO = 128, COL_O = 256;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc]
+__device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem desc]
+__device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+          "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]),
+          "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]),
+          "r"(v[30]), "r"(v[31])
+        : "memory");
+}
+__device__ __forceinline__ float ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): SWIZZLE_128B, version 1
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = f32, A = B = tf32
+__host__ __device__ constexpr uint32_t instr_desc(int m, int n, int b_mn_major) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+template <int D>
+__global__ void __launch_bounds__(kNumThreads, 1)
+softmax_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_r_hi, const __grid_constant__ CUtensorMap map_r_lo,
+                       const __grid_constant__ CUtensorMap map_c_hi, const __grid_constant__ CUtensorMap map_c_lo,
+                       int64_t n_r, int64_t n_c, const float *__restrict__ colscale, float offset, int n_split,
+                       float *__restrict__ rowsum_part, float *__restrict__ o_part) {
+    constexpr int KCH = D / 32;                         // 128-byte K chunks per row
+    constexpr uint32_t R_CHUNK = BM * 128, C_CHUNK = BN * 128;
+    constexpr uint32_t R_BYTES = KCH * R_CHUNK, C_BYTES = KCH * C_CHUNK;      // one precision part
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t *r_hi = smem, *r_lo = smem + R_BYTES;
+    uint8_t *c_base = smem + 2 * R_BYTES;               // stage s: hi at c_base + s*2*C_BYTES, lo right after
+    uint64_t *bars = reinterpret_cast<uint64_t *>(c_base + STAGES * 2 * C_BYTES);
+    uint64_t *full = bars, *empty = bars + STAGES, *s_full = bars + 2 * STAGES, *e_ready = s_full + 2;
+    uint64_t *r_full = e_ready + 2, *o_full = r_full + 1;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(o_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rt = blockIdx.x / n_split, sp = blockIdx.x % n_split;
+    const int64_t n_ct = (n_c + BN - 1) / BN;
+    const int t0 = (int)(n_ct * sp / n_split), t1 = (int)(n_ct * (sp + 1) / n_split);
+    const int n_tiles = t1 - t0;
+    const int row0 = rt * BM;
+
+    if (threadIdx.x == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_r_hi));
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_r_lo));
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_c_hi));
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_c_lo));
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&s_full[b], 1);
+            mbar_init(&e_ready[b], 128);
+        }
+        mbar_init(r_full, 1);
+        mbar_init(o_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0 && lane == 0) {
+        // ===================== TMA producer =====================
+        mbar_expect_tx(r_full, 2 * R_BYTES);
+        for (int c = 0; c < KCH; ++c) {
+            tma_load_2d(r_hi + c * R_CHUNK, &map_r_hi, c * 32, row0, r_full);
+            tma_load_2d(r_lo + c * R_CHUNK, &map_r_lo, c * 32, row0, r_full);
+        }
+        for (int i = 0; i < n_tiles; ++i) {
+            const int s = i % STAGES;
+            mbar_wait(&empty[s], ((i / STAGES) & 1) ^ 1);
+            uint8_t *hi = c_base + s * 2 * C_BYTES, *lo = hi + C_BYTES;
+            mbar_expect_tx(&full[s], 2 * C_BYTES);
+            for (int c = 0; c < KCH; ++c) {
+                tma_load_2d(hi + c * C_CHUNK, &map_c_hi, c * 32, (t0 + i) * BN, &full[s]);
+                tma_load_2d(lo + c * C_CHUNK, &map_c_lo, c * 32, (t0 + i) * BN, &full[s]);
+            }
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ===================== MMA issuer =====================
+        constexpr uint32_t idesc1 = instr_desc(BM, BN, 0);      // S[128 x 64]  = R (K-major)  x C (K-major)
+        constexpr uint32_t idesc2 = instr_desc(BM, D, 1);       // O[128 x D ] += E (TMEM)     x C (MN-major)
+        const uint32_t r_hi_a = smem_u32(r_hi), r_lo_a = smem_u32(r_lo);
+        auto gemm2 = [&](int j) {
+            const int s = j % STAGES, b = j & 1;
+            const uint32_t c_hi_a = smem_u32(c_base + s * 2 * C_BYTES), c_lo_a = c_hi_a + C_BYTES;
+            const uint32_t e_hi = tmem + COL_SE + b * BN, e_lo = tmem + COL_ELO + b * BN;
+#pragma unroll
+            for (int part = 0; part < 3; ++part) {
+                const uint32_t ea = (part == 1) ? e_lo : e_hi;
+                const uint32_t cb = (part == 2) ? c_lo_a : c_hi_a;
+#pragma unroll
+                for (int ks = 0; ks < BN / 8; ++ks) {
+                    // B: 8 rows (K) x D floats (N, contiguous): MN-major, 128-byte chunks C_CHUNK apart
+                    const uint64_t bd = smem_desc(cb + ks * 1024, C_CHUNK, 1024);
+                    mma_ts(tmem + COL_O, ea + ks * 8, bd, idesc2, (j > 0 || part > 0 || ks > 0) ? 1u : 0u);
+                }
+            }
+            tc_commit(&empty[s]);                               // stage free once GEMM2 has read it
+        };
+        mbar_wait(r_full, 0);
+        for (int i = 0; i < n_tiles; ++i) {
+            const int s = i % STAGES, b = i & 1;
+            mbar_wait(&full[s], (i / STAGES) & 1);
+            tc_fence_after();
+            const uint32_t c_hi_a = smem_u32(c_base + s * 2 * C_BYTES), c_lo_a = c_hi_a + C_BYTES;
+#pragma unroll
+            for (int part = 0; part < 3; ++part) {
+                const uint32_t ra = (part == 1) ? r_lo_a : r_hi_a;
+                const uint32_t cb = (part == 2) ? c_lo_a : c_hi_a;
+#pragma unroll
+                for (int c = 0; c < KCH; ++c)
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {
+                        const uint64_t ad = smem_desc(ra + c * R_CHUNK + ks * 32, 16, 1024);
+                        const uint64_t bd = smem_desc(cb + c * C_CHUNK + ks * 32, 16, 1024);
+                        mma_ss(tmem + COL_SE + b * BN, ad, bd, idesc1, (part > 0 || c > 0 || ks > 0) ? 1u : 0u);
+                    }
+            }
+            tc_commit(&s_full[b]);
+            if (i > 0) {
+                mbar_wait(&e_ready[(i - 1) & 1], ((i - 1) >> 1) & 1);
+                tc_fence_after();
+                gemm2(i - 1);
+            }
+        }
+        if (n_tiles > 0) {
+            const int j = n_tiles - 1;
+            mbar_wait(&e_ready[j & 1], (j >> 1) & 1);
+            tc_fence_after();
+            gemm2(j);
+        }
+        tc_commit(o_full);
+    } else if (warp >= 4) {
+        // ===================== epilogue: thread = TMEM lane = row =====================
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
+        float rowsum = 0.f;
+        for (int i = 0; i < n_tiles; ++i) {
+            const int b = i & 1;
+            mbar_wait(&s_full[b], (i >> 1) & 1);
+            tc_fence_after();
+            const int64_t col0 = (int64_t)(t0 + i) * BN;
+#pragma unroll
+            for (int h = 0; h < BN / 32; ++h) {
+                uint32_t v[32], lo[32];
+                tmem_ld32(lane_base + COL_SE + b * BN + h * 32, v);
+#pragma unroll
+                for (int k = 0; k < 32; k += 4) {
+                    float cs[4] = {1.f, 1.f, 1.f, 1.f};
+                    if (colscale != nullptr) {
+                        const float4 c4 = __ldg(reinterpret_cast<const float4 *>(colscale + col0 + h * 32 + k));
+                        cs[0] = c4.x; cs[1] = c4.y; cs[2] = c4.z; cs[3] = c4.w;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const bool valid = col0 + h * 32 + k + u < n_c;
+                        const float e = valid ? ex2(__uint_as_float(v[k + u]) - offset) * cs[u] : 0.f;
+                        rowsum += e;
+                        const uint32_t hi = __float_as_uint(e) & 0xffffe000u;      // tf32(e), truncated
+                        v[k + u] = hi;
+                        lo[k + u] = __float_as_uint(e - __uint_as_float(hi));
+                    }
+                }
+                tmem_st32(lane_base + COL_SE + b * BN + h * 32, v);                 // E_hi over S, in place
+                tmem_st32(lane_base + COL_ELO + b * BN + h * 32, lo);
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            tc_fence_before();
+            mbar_arrive(&e_ready[b]);
+        }
+        // ---- O and the row sums: once per CTA ----
+        mbar_wait(o_full, 0);
+        tc_fence_after();
+        const int64_t grow = (int64_t)row0 + row;
+        if (n_tiles > 0) {
+#pragma unroll
+            for (int h = 0; h < D / 32; ++h) {
+                uint32_t v[32];
+                tmem_ld32(lane_base + COL_O + h * 32, v);
+                if (grow < n_r) {
+                    float4 *dst = reinterpret_cast<float4 *>(o_part + ((size_t)sp * n_r + grow) * D + h * 32);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        dst[k] = make_float4(__uint_as_float(v[4 * k]), __uint_as_float(v[4 * k + 1]), __uint_as_float(v[4 * k + 2]),
+                                             __uint_as_float(v[4 * k + 3]));
+                }
+            }
+        } else if (grow < n_r) {
+            for (int k = 0; k < D; ++k) o_part[((size_t)sp * n_r + grow) * D + k] = 0.f;
+        }
+        if (grow < n_r && rowsum_part != nullptr) rowsum_part[(size_t)sp * n_r + grow] = rowsum;
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols) : "memory");
+    }
+}
+
+// ---- host side: tensor maps through the driver entry point (no link-time libcuda dependency) ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn == nullptr) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// [rows, dim] fp32 row-major -> boxes of 32 floats (128 B, SWIZZLE_128B) x box_rows rows; rows beyond n read as 0
+int make_map(CUtensorMap *map, const float *base, int64_t rows, int dim, int box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (fn == nullptr) {
+        ssl::set_error("cuTensorMapEncodeTiled is not available from this driver");
+        return SSL_E_CUDA;
+    }
+    cuuint64_t gdim[2] = {(cuuint64_t)dim, (cuuint64_t)rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)dim * sizeof(float)};
+    cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1u, 1u};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        ssl::set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+        return SSL_E_CUDA;
+    }
+    return SSL_OK;
+}
+
+template <int D>
+int launch_tc(const float *R_hi, const float *R_lo, int64_t n_r, const float *C_hi, const float *C_lo, int64_t n_c,
+              const float *colscale, float offset, int n_split, float *rowsum_part, float *o_part, cudaStream_t st) {
+    CUtensorMap mr_hi, mr_lo, mc_hi, mc_lo;
+    int rc;
+    if ((rc = make_map(&mr_hi, R_hi, n_r, D, BM)) != SSL_OK) return rc;
+    if ((rc = make_map(&mr_lo, R_lo, n_r, D, BM)) != SSL_OK) return rc;
+    if ((rc = make_map(&mc_hi, C_hi, n_c, D, BN)) != SSL_OK) return rc;
+    if ((rc = make_map(&mc_lo, C_lo, n_c, D, BN)) != SSL_OK) return rc;
+    constexpr int KCH = D / 32;
+    const size_t smem = 1024 + 2 * (size_t)KCH * BM * 128 + (size_t)STAGES * 2 * KCH * BN * 128 + 16 * sizeof(uint64_t);
+    static bool configured = false;
+    if (!configured) {
+        SSL_CUDA(cudaFuncSetAttribute(softmax_gemm_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    const int64_t grid = ((n_r + BM - 1) / BM) * n_split;
+    softmax_gemm_tc_kernel<D><<<(unsigned)grid, kNumThreads, smem, st>>>(mr_hi, mr_lo, mc_hi, mc_lo, n_r, n_c, colscale, offset, n_split,
+                                                                         rowsum_part, o_part);
+    SSL_LAUNCH_CHECK("softmax_gemm_tc_kernel");
+    return SSL_OK;
+}
+
+}  // namespace
+
+extern "C" int ssl_softmax_gemm_tf32x3(const float *R_hi, const float *R_lo, int64_t n_r, const float *C_hi, const float *C_lo,
+                                       int64_t n_c, int32_t dim, const float *colscale, float offset, int32_t n_split,
+                                       float *rowsum_part, float *o_part, void *stream) {
+    SSL_CHECK_ARG(R_hi && R_lo && C_hi && C_lo && o_part, "ssl_softmax_gemm_tf32x3: null argument");
+    SSL_CHECK_ARG(dim == 32 || dim == 64, "ssl_softmax_gemm_tf32x3: dim %d not supported (32 or 64; other sizes use ssl_softmax_gemm)", dim);
+    SSL_CHECK_ARG((n_split >= 1 && n_split <= (n_c + BN - 1) / BN) || n_c == 0, "ssl_softmax_gemm_tf32x3: n_split %d exceeds the number of C tiles", n_split);
+    SSL_CHECK_ARG(((reinterpret_cast<uintptr_t>(R_hi) | reinterpret_cast<uintptr_t>(R_lo) | reinterpret_cast<uintptr_t>(C_hi) |
+                    reinterpret_cast<uintptr_t>(C_lo) | reinterpret_cast<uintptr_t>(o_part)) & 15) == 0,
+                  "ssl_softmax_gemm_tf32x3: operands must be 16-byte aligned");
+    if (n_r == 0 || n_c == 0) return SSL_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dim == 32) return launch_tc<32>(R_hi, R_lo, n_r, C_hi, C_lo, n_c, colscale, offset, n_split, rowsum_part, o_part, st);
+    return launch_tc<64>(R_hi, R_lo, n_r, C_hi, C_lo, n_c, colscale, offset, n_split, rowsum_part, o_part, st);
+}

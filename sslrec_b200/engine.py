@@ -26,6 +26,9 @@ from ._lib import PropArgs, check, lib
 from .graph import GraphPlan
 
 LOG2E = 1.4426950408889634
+# InfoNCE contraction on tcgen05 (3xTF32, fp32-grade accuracy) when the dim allows; set to False to force the
+# FP32-FMA kernel (tests compare the two)
+USE_TENSOR_CORES = True
 
 
 def _stream(t: torch.Tensor) -> int:
@@ -587,7 +590,8 @@ def _nce_fwd(e1: Rows, e2: Rows, table: Rows, idx, idx2, tau, norm_mode, mean, d
     B, n = idx.numel(), table.n
     Bp, npad = ceil_to(B, 64), ceil_to(n, 64)
     f = dict(device=dev, dtype=torch.float32)
-    a_hat, a_t, rinv1 = torch.empty(Bp, d, **f), torch.empty(Bp // 64, d, 64, **f), torch.empty(B, **f)
+    a_hat, rinv1 = torch.empty(Bp, d, **f), torch.empty(B, **f)
+    a_t = torch.empty(Bp // 64, d, 64, **f)
     p_hat, rinv2 = torch.empty(Bp, d, **f), torch.empty(B, **f)
     comm = table.comm
     full_table = table
@@ -596,22 +600,34 @@ def _nce_fwd(e1: Rows, e2: Rows, table: Rows, idx, idx2, tau, norm_mode, mean, d
         table = table.sub(lo, hi)
         n = table.n
         npad = max(64, ceil_to(n, 64))
-    t_hat, t_t, rinv_t = torch.empty(npad, d, **f), torch.empty(npad // 64, d, 64, **f), torch.empty(max(n, 1), **f)
-    n_split = choose_split((B + 127) // 128, npad // 64)
+    use_tc = USE_TENSOR_CORES and d in (32, 64)     # tcgen05 3xTF32 contraction; other dims run the FFMA kernel
+    t_hat, rinv_t = torch.empty(npad, d, **f), torch.empty(max(n, 1), **f)
+    if use_tc:
+        a_t = t_t = None
+        a_hi, a_lo = torch.empty(Bp, d, **f), torch.empty(Bp, d, **f)
+        t_hi, t_lo = torch.empty(npad, d, **f), torch.empty(npad, d, **f)
+    else:
+        t_t = torch.empty(npad // 64, d, 64, **f)
+        a_hi = a_lo = t_hi = t_lo = None
+    n_split = choose_split((B + 127) // 128, npad // 64, slots=148 if use_tc else 296)
     rs_part, o_part = torch.zeros(n_split, B, **f), torch.zeros(n_split, B, d, **f)
     rowsum, obar, loss_b, out = torch.empty(B, **f), torch.empty(B, d, **f), torch.empty(B, **f), torch.empty((), **f)
     off = LOG2E / tau
     with torch.cuda.device(dev):
         s = _stream(table.base)
         check(lib.ssl_rows_normalize(e1.ptr, e1.stride, idx.data_ptr(), B, d, norm_mode, off, a_hat.data_ptr(),
-                                     a_t.data_ptr(), rinv1.data_ptr(), s), 'ssl_rows_normalize(e1)')
+                                     _ptr(a_t), rinv1.data_ptr(), _ptr(a_hi), _ptr(a_lo), s), 'ssl_rows_normalize(e1)')
         check(lib.ssl_rows_normalize(e2.ptr, e2.stride, idx2.data_ptr(), B, d, norm_mode, 1.0, p_hat.data_ptr(), None,
-                                     rinv2.data_ptr(), s), 'ssl_rows_normalize(e2)')
+                                     rinv2.data_ptr(), None, None, s), 'ssl_rows_normalize(e2)')
         check(lib.ssl_rows_normalize(table.ptr, table.stride, None, n, d, norm_mode, 1.0, t_hat.data_ptr(),
-                                     t_t.data_ptr(), rinv_t.data_ptr(), s), 'ssl_rows_normalize(table)')
-        with _timed('nce_gemm_fwd', dict(B=B, n=n, dim=d)):
-            check(lib.ssl_softmax_gemm(a_hat.data_ptr(), B, t_hat.data_ptr(), t_t.data_ptr(), n, d, None, off, n_split,
-                                       rs_part.data_ptr(), o_part.data_ptr(), s), 'ssl_softmax_gemm(fwd)')
+                                     _ptr(t_t), rinv_t.data_ptr(), _ptr(t_hi), _ptr(t_lo), s), 'ssl_rows_normalize(table)')
+        with _timed('nce_gemm_fwd', dict(B=B, n=n, dim=d, tc=use_tc)):
+            if use_tc:
+                check(lib.ssl_softmax_gemm_tf32x3(a_hi.data_ptr(), a_lo.data_ptr(), B, t_hi.data_ptr(), t_lo.data_ptr(), n, d, None, off,
+                                                  n_split, rs_part.data_ptr(), o_part.data_ptr(), s), 'ssl_softmax_gemm_tf32x3(fwd)')
+            else:
+                check(lib.ssl_softmax_gemm(a_hat.data_ptr(), B, t_hat.data_ptr(), t_t.data_ptr(), n, d, None, off, n_split,
+                                           rs_part.data_ptr(), o_part.data_ptr(), s), 'ssl_softmax_gemm(fwd)')
         if comm is not None:
             red = torch.cat([o_part.sum(0), rs_part.sum(0).unsqueeze(1)], 1)         # [B, d+1]
             comm.allreduce_sum(red)
@@ -620,12 +636,13 @@ def _nce_fwd(e1: Rows, e2: Rows, table: Rows, idx, idx2, tau, norm_mode, mean, d
                                    tau, deno_eps * math.exp(-1.0 / tau), rowsum.data_ptr(), obar.data_ptr(),
                                    loss_b.data_ptr(), s), 'ssl_nce_finalize')
         check(lib.ssl_sum(loss_b.data_ptr(), B, (1.0 / B) if mean else 1.0, out.data_ptr(), s), 'ssl_sum')
-    saved = (e1, e2, table, idx, tau, mean, a_hat, a_t, p_hat, rinv1, rinv2, t_hat, rinv_t, rowsum, obar, full_table, comm)
+    saved = (e1, e2, table, idx, tau, mean, a_hat, a_t, p_hat, rinv1, rinv2, t_hat, rinv_t, rowsum, obar, full_table, comm,
+             (a_hi, a_lo, t_hi, t_lo) if use_tc else None)
     return out, saved
 
 
 def _nce_bwd(saved, g):
-    (e1, e2, table, idx, tau, mean, a_hat, a_t, p_hat, rinv1, rinv2, t_hat, rinv_t, rowsum, obar, full_table, comm) = saved
+    (e1, e2, table, idx, tau, mean, a_hat, a_t, p_hat, rinv1, rinv2, t_hat, rinv_t, rowsum, obar, full_table, comm, tc) = saved
     dev, d = g.device, table.dim
     B, n = idx.numel(), table.n
     g = g.contiguous()
@@ -646,11 +663,17 @@ def _nce_bwd(saved, g):
         if gt is not None and n > 0:
             colscale = torch.empty(ceil_to(B, 64), **f)
             check(lib.ssl_nce_colscale(rowsum.data_ptr(), B, g.data_ptr(), scale, colscale.data_ptr(), s), 'ssl_nce_colscale')
-            n_split = choose_split((n + 127) // 128, ceil_to(B, 64) // 64)
+            n_split = choose_split((n + 127) // 128, ceil_to(B, 64) // 64, slots=148 if tc else 296)
             dt_part = torch.empty(n_split, n, d, **f)
-            with _timed('nce_gemm_bwd', dict(B=B, n=n, dim=d)):
-                check(lib.ssl_softmax_gemm(t_hat.data_ptr(), n, a_hat.data_ptr(), a_t.data_ptr(), B, d, colscale.data_ptr(),
-                                           LOG2E / tau, n_split, None, dt_part.data_ptr(), s), 'ssl_softmax_gemm(bwd)')
+            with _timed('nce_gemm_bwd', dict(B=B, n=n, dim=d, tc=bool(tc))):
+                if tc:
+                    a_hi, a_lo, t_hi, t_lo = tc
+                    check(lib.ssl_softmax_gemm_tf32x3(t_hi.data_ptr(), t_lo.data_ptr(), n, a_hi.data_ptr(), a_lo.data_ptr(), B, d,
+                                                      colscale.data_ptr(), LOG2E / tau, n_split, None, dt_part.data_ptr(), s),
+                          'ssl_softmax_gemm_tf32x3(bwd)')
+                else:
+                    check(lib.ssl_softmax_gemm(t_hat.data_ptr(), n, a_hat.data_ptr(), a_t.data_ptr(), B, d, colscale.data_ptr(),
+                                               LOG2E / tau, n_split, None, dt_part.data_ptr(), s), 'ssl_softmax_gemm(bwd)')
             check(lib.ssl_nce_bwd_table(dt_part.data_ptr(), n_split, t_hat.data_ptr(), rinv_t.data_ptr(), n, d, gt,
                                         gt_stride, 1, s), 'ssl_nce_bwd_table')
         if local_dt is not None:

@@ -142,9 +142,13 @@ def test_node_drop_forward_backward():
     H.close(de0, e0r.grad, 1e-5, 1e-5, 'dE0 with node drop')
 
 
-@pytest.mark.parametrize('dim,B,n', [(64, 4096, 9000), (32, 100, 777), (128, 300, 2000), (48, 257, 1000), (64, 64, 50)])
-def test_infonce_term_forward_backward(dim, B, n):
+@pytest.mark.parametrize('use_tc', [True, False])
+@pytest.mark.parametrize('dim,B,n', [(64, 4096, 9000), (32, 100, 777), (128, 300, 2000), (48, 257, 1000), (64, 64, 50), (64, 130, 64 * 9 + 1)])
+def test_infonce_term_forward_backward(dim, B, n, use_tc, monkeypatch):
+    """use_tc: the tcgen05 3xTF32 contraction (dims 32 / 64) vs the FP32-FMA kernel -- same tolerances."""
+    from sslrec_b200 import engine
     from sslrec_b200 import loss_utils as LU
+    monkeypatch.setattr(engine, 'USE_TENSOR_CORES', use_tc)
     g = torch.Generator().manual_seed(6)
     e1 = torch.randn(B, dim, generator=g)
     e2 = torch.randn(B, dim, generator=g)
