@@ -161,7 +161,8 @@ SSL_API int ssl_bpr_bwd(const float *users, int64_t u_stride, const float *items
  *   output (alpha), writes row-major out [n, dim], the K-major tile copy out_t
  *   [ceil(n/64), dim, 64] the streaming side of ssl_softmax_gemm reads (may be NULL),
  *   rinv [n] (the 1/norm used, needed by the backward), and optionally the tf32 split
- *   out_hi = tf32(out), out_lo = out - out_hi (row-major [n, dim] each) that
+ *   out_hi = tf32(out), out_lo = out - out_hi, row-major [n, dim] each, plus their transposes
+ *   out_thi / out_tlo [dim, t_pitch] (t_pitch >= ceil64(n), multiple of 4) that
  *   ssl_softmax_gemm_tf32x3 reads through TMA.
  * ssl_softmax_gemm    for every row r of R [n_r, dim] over the rows c of C (row-major C
  *   [n_c, dim] and its K-major tile copy C_t):   e = exp2(R_r . C_c - offset) * colscale[c]
@@ -172,16 +173,19 @@ SSL_API int ssl_bpr_bwd(const float *users, int64_t u_stride, const float *items
  *   (R = table tile, C = anchors, colscale = g/rowsum: the dense table gradient).
  * ------------------------------------------------------------------------------------------ */
 SSL_API int ssl_rows_normalize(const float *x, int64_t stride, const int64_t *idx, int64_t n, int32_t dim, int32_t norm_mode,
-                       float alpha, float *out, float *out_t, float *rinv, float *out_hi, float *out_lo, void *stream);
+                       float alpha, float *out, float *out_t, float *rinv, float *out_hi, float *out_lo,
+                       float *out_thi, float *out_tlo, int64_t t_pitch, void *stream);
 SSL_API int ssl_softmax_gemm(const float *R, int64_t n_r, const float *C, const float *C_t, int64_t n_c, int32_t dim,
                      const float *colscale, float offset, int32_t n_split, float *rowsum_part, float *o_part,
                      void *stream);
 /* The same contraction on the tcgen05 tensor cores with 3xTF32 error compensation (fp32-grade
- * accuracy): operands are the hi / lo splits written by ssl_rows_normalize, row-major [n, dim];
+ * accuracy): operands are the hi / lo splits written by ssl_rows_normalize, row-major [n, dim],
+ * and for the streamed operand also the transposed splits CT_hi / CT_lo [dim, ct_pitch];
  * dim must be 32 or 64.  Outputs and semantics are those of ssl_softmax_gemm. */
 SSL_API int ssl_softmax_gemm_tf32x3(const float *R_hi, const float *R_lo, int64_t n_r, const float *C_hi, const float *C_lo,
-                            int64_t n_c, int32_t dim, const float *colscale, float offset, int32_t n_split,
-                            float *rowsum_part, float *o_part, void *stream);
+                            const float *CT_hi, const float *CT_lo, int64_t ct_pitch, int64_t n_c, int32_t dim,
+                            const float *colscale, float offset, int32_t n_split, float *rowsum_part, float *o_part,
+                            void *stream);
 /* forward epilogue of one term: reduces the split partials and produces, per anchor b,
  *   rowsum[b] (+ deno_eps), obar[b,:] = o[b,:]/rowsum[b] and
  *   loss_b[b] = -(a^_b . p^_b)/tau + 1/tau + ln(rowsum[b])          */

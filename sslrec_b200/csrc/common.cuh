@@ -89,6 +89,18 @@ __host__ __device__ __forceinline__ float4 noise_u4_rng(uint64_t seed, uint32_t 
     return make_float4(u01(r.x), u01(r.y), u01(r.z), u01(r.w));
 }
 
+// 3xTF32 split: hi = round-to-nearest tf32(x), lo = round-to-nearest tf32(x - hi).  Rounding (not
+// truncating) both parts keeps the residual |x - hi - lo| <= 2^-22 |x| and unbiased.
+__device__ __forceinline__ float tf32_rna(float x) {
+    uint32_t y;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(y) : "f"(x));
+    return __uint_as_float(y);
+}
+__device__ __forceinline__ void tf32_split(float x, float &hi, float &lo) {
+    hi = tf32_rna(x);
+    lo = tf32_rna(x - hi);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -76,7 +76,8 @@ __global__ void bpr_bwd_kernel(const float *users, int64_t us, const float *item
 __global__ void __launch_bounds__(256) rows_normalize_kernel(const float *__restrict__ x, int64_t stride, const int64_t *__restrict__ idx,
                                                            int64_t n, int dim, int mode, float alpha, float *__restrict__ out,
                                                            float *__restrict__ out_t, float *__restrict__ rinv,
-                                                           float *__restrict__ out_hi, float *__restrict__ out_lo) {
+                                                           float *__restrict__ out_hi, float *__restrict__ out_lo,
+                                                           float *__restrict__ out_thi, float *__restrict__ out_tlo, int64_t t_pitch) {
     extern __shared__ float tile[];   // [64][dim + 1]
     const int pitch = dim + 1;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -107,20 +108,32 @@ __global__ void __launch_bounds__(256) rows_normalize_kernel(const float *__rest
                 tile[lr * pitch + k] = y;
                 out[row * dim + k] = y;            // rows n .. ceil64(n) are written as zeros
                 if (out_hi != nullptr) {           // tf32 split for the tensor-core contraction
-                    const float hi = __uint_as_float(__float_as_uint(y) & 0xffffe000u);
+                    float hi, lo;
+                    ssl::tf32_split(y, hi, lo);
                     out_hi[row * dim + k] = hi;
-                    out_lo[row * dim + k] = y - hi;
+                    out_lo[row * dim + k] = lo;
                 }
             }
         }
     }
-    if (out_t == nullptr) return;
+    if (out_t == nullptr && out_thi == nullptr) return;
     __syncthreads();
-    float *dst = out_t + (size_t)blockIdx.x * dim * 64;
-    for (int i = threadIdx.x; i < dim * 64; i += 256) {
-        const int k = i >> 6, q = i & 63;
-        const int c = (q >> 2) + 16 * (q & 3);
-        dst[i] = tile[c * pitch + k];
+    if (out_t != nullptr) {
+        float *dst = out_t + (size_t)blockIdx.x * dim * 64;
+        for (int i = threadIdx.x; i < dim * 64; i += 256) {
+            const int k = i >> 6, q = i & 63;
+            const int c = (q >> 2) + 16 * (q & 3);
+            dst[i] = tile[c * pitch + k];
+        }
+    }
+    if (out_thi != nullptr) {       // transposed tf32 split: [dim, t_pitch], 64 consecutive columns per block
+        for (int i = threadIdx.x; i < dim * 64; i += 256) {
+            const int k = i >> 6, c = i & 63;
+            float hi, lo;
+            ssl::tf32_split(tile[c * pitch + k], hi, lo);
+            out_thi[(size_t)k * t_pitch + row0 + c] = hi;
+            out_tlo[(size_t)k * t_pitch + row0 + c] = lo;
+        }
     }
 }
 
@@ -390,14 +403,16 @@ extern "C" int ssl_bpr_bwd(const float *users, int64_t u_stride, const float *it
 }
 
 extern "C" int ssl_rows_normalize(const float *x, int64_t stride, const int64_t *idx, int64_t n, int32_t dim, int32_t norm_mode,
-                                  float alpha, float *out, float *out_t, float *rinv, float *out_hi, float *out_lo, void *stream) {
+                                  float alpha, float *out, float *out_t, float *rinv, float *out_hi, float *out_lo,
+                                  float *out_thi, float *out_tlo, int64_t t_pitch, void *stream) {
     SSL_CHECK_ARG(x && out, "ssl_rows_normalize: null argument");
-    SSL_CHECK_ARG((out_hi == nullptr) == (out_lo == nullptr), "ssl_rows_normalize: out_hi and out_lo go together");
+    SSL_CHECK_ARG((out_hi == nullptr) == (out_lo == nullptr) && (out_thi == nullptr) == (out_tlo == nullptr), "ssl_rows_normalize: hi and lo outputs go together");
+    SSL_CHECK_ARG(out_thi == nullptr || (t_pitch >= (n + 63) / 64 * 64 && t_pitch % 4 == 0), "ssl_rows_normalize: t_pitch must be >= ceil64(n) and a multiple of 4");
     SSL_CHECK_ARG(dim >= 4 && dim <= SSL_MAX_DIM && dim % 4 == 0, "ssl_rows_normalize: dim %d must be a multiple of 4 <= %d", dim, SSL_MAX_DIM);
     SSL_CHECK_ARG(norm_mode == 0 || norm_mode == 1, "ssl_rows_normalize: bad norm_mode");
     if (n == 0) return SSL_OK;
     const size_t smem = sizeof(float) * 64 * (dim + 1);
-    rows_normalize_kernel<<<(unsigned)((n + 63) / 64), 256, smem, STREAM>>>(x, stride, idx, n, dim, norm_mode, alpha, out, out_t, rinv, out_hi, out_lo);
+    rows_normalize_kernel<<<(unsigned)((n + 63) / 64), 256, smem, STREAM>>>(x, stride, idx, n, dim, norm_mode, alpha, out, out_t, rinv, out_hi, out_lo, out_thi, out_tlo, t_pitch);
     SSL_LAUNCH_CHECK("rows_normalize_kernel");
     return SSL_OK;
 }

@@ -6,32 +6,39 @@
 //   O += E C     = E_hi C_hi   + E_lo C_hi   + E_hi C_lo
 //
 // Same contract as ssl_softmax_gemm (nce_gemm.cu): one launch is the forward of an InfoNCE term or,
-// with the operand roles swapped, its backward.  The dropped lo*lo products and the tf32 truncation
-// of the lo parts are O(2^-21) relative -- the fp32 rounding level of the FFMA kernel.
+// with the operand roles swapped, its backward.  Both parts are rounded to nearest (cvt.rna.tf32), so the
+// dropped lo*lo products and the rounding of the lo parts are O(2^-22) relative and unbiased -- the fp32
+// rounding level of the FFMA kernel.
 //
 // Structure (one CTA per SM, 256 threads, warp-specialised, all synchronisation by mbarriers):
-//   warp 0 / lane 0 : TMA producer.  2-D tensor maps (SWIZZLE_128B, 32-float boxes) over the
-//                     row-major hi / lo operand arrays; the resident 128-row R tile once, the 64-row
-//                     C tiles through a 4-stage ring.
-//   warp 1 / lane 0 : MMA issuer.  GEMM1 (M=128, N=64, K=d): both operands K-major in shared memory
-//                     -> S in TMEM.  GEMM2 (M=128, N=d, K=64): A = E read from TENSOR MEMORY, B = the
-//                     SAME C tile addressed MN-major -> O in TMEM, accumulated over all tiles.
-//                     Issue order MMA1(t), MMA2(t-1): the tensor pipe works on tile t while the
-//                     epilogue warps process tile t-1.
-//   warps 4-7       : epilogue, thread = TMEM lane = row.  tcgen05.ld S, ex2, row sums in registers
-//                     (no cross-thread reduction), split E into hi / lo, tcgen05.st them back into
-//                     TMEM (E_hi over S in place); finally O is read out of TMEM once per CTA.
-//   TMEM columns    : [0,128) S/E_hi x2 buffers, [128,256) E_lo x2 buffers, [256,256+d) O.
+//   warp 0 / lane 0 : TMA producer, ring 1.  2-D tensor maps (SWIZZLE_128B, 32-float boxes) over the
+//                     row-major hi / lo operand arrays: the resident 128-row R tile once, then the 64-row
+//                     C tiles (GEMM1's B operand, K-major; freed as soon as GEMM1 of the tile retires).
+//   warp 2 / lane 0 : TMA producer, ring 2: the same tiles from the TRANSPOSED copies [d, n] (GEMM2's B
+//                     operand, K-major again).  tf32 operands must be K-major here: an MN-major view of
+//                     the row-major tile needs the 32-byte-atom swizzle, which the K-major GEMM1 view of
+//                     the same bytes cannot share (measured: the MN-major descriptor yields zeros).
+//   warp 1 / lane 0 : MMA issuer 1.  GEMM1 (M=128, N=64, K=d): both operands in shared memory -> S in TMEM.
+//   warp 3 / lane 0 : MMA issuer 2.  GEMM2 (M=128, N=d, K=64): A = E read from TENSOR MEMORY, B = C^T tile ->
+//                     O in TMEM, accumulated over all tiles.  Two issuing threads because tf32 MMAs are only
+//                     K = 8 deep: one thread cannot issue them as fast as the tensor pipe retires them.
+//   warps 4-7, 8-11 : two epilogue warpgroups ping-ponging over the tiles (parity), thread = TMEM lane =
+//                     row.  tcgen05.ld S, ex2, row sums in registers (no cross-thread reduction), split E
+//                     into hi / lo, tcgen05.st them back into TMEM (E_hi over S in place); finally O is
+//                     read out of TMEM once per CTA.
+//   TMEM columns    : [0,128) S/E_hi x2 buffers, [128,256) E_lo x2 buffers, [256,256+d) O (hi*hi),
+//                     [384,384+d) O correction terms.
 #include <cuda.h>
+#include <cstdlib>
 
 #include "common.cuh"
 
 namespace {
 
-constexpr int BM = 128, BN = 64, STAGES = 4;
-constexpr int kNumThreads = 256;
+constexpr int BM = 128, BN = 64, STAGES = 2;
+constexpr int kNumThreads = 384;       // warps 0-3: TMA x2, MMA, spare; warps 4-7 and 8-11: two epilogue warpgroups
 constexpr uint32_t kTmemCols = 512;
-constexpr uint32_t COL_SE = 0, COL_ELO = 128, COL_O = 256;
+constexpr uint32_t COL_SE = 0, COL_ELO = 128, COL_O = 256, COL_OC = 384;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -59,6 +66,18 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, i
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
+// exactly one lane of a fully converged warp (warp-uniform control flow around it keeps the operands of
+// the MMA / commit instructions in uniform registers: no per-lane "waterfall" loop around every UTCHMMA)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t *bar) {
@@ -81,6 +100,47 @@ __device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_
         "setp.ne.b32 p, %4, 0;\n"
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
         "}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// Four consecutive K-steps (one 128-byte swizzle chunk = 32 tf32) in ONE asm block: the descriptors advance by
+// 32 bytes (+2 in the 16-byte-unit address field) inside the block, so the single issuing thread spends ~3
+// instructions per MMA instead of ~15 (ncu round 1: the contraction was bound by the MMA issue loop, not by the
+// tensor pipe).  acc_first: whether the first of the four accumulates onto D; the other three always do.
+__device__ __forceinline__ void mma_ss_x4(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc_first) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p, t;\n"
+        ".reg .b64 a, b;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "setp.eq.b32 t, 0, 0;\n"
+        "mov.b64 a, %1;\n"
+        "mov.b64 b, %2;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], a, b, %3, p;\n"
+        "add.s64 a, a, 2;\n add.s64 b, b, 2;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], a, b, %3, t;\n"
+        "add.s64 a, a, 2;\n add.s64 b, b, 2;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], a, b, %3, t;\n"
+        "add.s64 a, a, 2;\n add.s64 b, b, 2;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], a, b, %3, t;\n"
+        "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc_first) : "memory");
+}
+__device__ __forceinline__ void mma_ts_x4(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc_first) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p, t;\n"
+        ".reg .b64 b;\n"
+        ".reg .b32 a;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "setp.eq.b32 t, 0, 0;\n"
+        "mov.b32 a, %1;\n"
+        "mov.b64 b, %2;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [a], b, %3, p;\n"
+        "add.s32 a, a, 8;\n add.s64 b, b, 2;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [a], b, %3, t;\n"
+        "add.s32 a, a, 8;\n add.s64 b, b, 2;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [a], b, %3, t;\n"
+        "add.s32 a, a, 8;\n add.s64 b, b, 2;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [a], b, %3, t;\n"
+        "}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc_first) : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
@@ -119,23 +179,51 @@ __host__ __device__ constexpr uint32_t instr_desc(int m, int n, int b_mn_major) 
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
+// one 32-column chunk of a tile: S -> E, row sum, tf32 split
+template <bool CHECK>
+__device__ __forceinline__ void exp_chunk(uint32_t (&v)[32], uint32_t (&lo)[32], float offset, const float *__restrict__ cs_ptr,
+                                          int64_t col, int64_t n_c, float &rowsum) {
+#pragma unroll
+    for (int k = 0; k < 32; k += 4) {
+        float cs[4] = {1.f, 1.f, 1.f, 1.f};
+        if (cs_ptr != nullptr) {
+            const float4 c4 = __ldg(reinterpret_cast<const float4 *>(cs_ptr + col + k));
+            cs[0] = c4.x; cs[1] = c4.y; cs[2] = c4.z; cs[3] = c4.w;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            float e = ex2(__uint_as_float(v[k + u]) - offset) * cs[u];
+            if (CHECK) e = (col + k + u < n_c) ? e : 0.f;
+            rowsum += e;
+            float ehi, elo;
+            ssl::tf32_split(e, ehi, elo);
+            v[k + u] = __float_as_uint(ehi);
+            lo[k + u] = __float_as_uint(elo);
+        }
+    }
+}
+
 template <int D>
 __global__ void __launch_bounds__(kNumThreads, 1)
 softmax_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_r_hi, const __grid_constant__ CUtensorMap map_r_lo,
                        const __grid_constant__ CUtensorMap map_c_hi, const __grid_constant__ CUtensorMap map_c_lo,
+                       const __grid_constant__ CUtensorMap map_ct_hi, const __grid_constant__ CUtensorMap map_ct_lo,
                        int64_t n_r, int64_t n_c, const float *__restrict__ colscale, float offset, int n_split,
                        float *__restrict__ rowsum_part, float *__restrict__ o_part) {
-    constexpr int KCH = D / 32;                         // 128-byte K chunks per row
-    constexpr uint32_t R_CHUNK = BM * 128, C_CHUNK = BN * 128;
-    constexpr uint32_t R_BYTES = KCH * R_CHUNK, C_BYTES = KCH * C_CHUNK;      // one precision part
+    constexpr int KCH = D / 32;                         // 128-byte K chunks per operand row (GEMM1: K = d)
+    constexpr int JCH = BN / 32;                        // 128-byte K chunks of the transposed tile (GEMM2: K = 64 rows)
+    constexpr uint32_t R_CHUNK = BM * 128, C_CHUNK = BN * 128, T_CHUNK = D * 128;
+    constexpr uint32_t R_BYTES = KCH * R_CHUNK, C_BYTES = KCH * C_CHUNK, T_BYTES = JCH * T_CHUNK;   // one precision part
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t *r_hi = smem, *r_lo = smem + R_BYTES;
-    uint8_t *c_base = smem + 2 * R_BYTES;               // stage s: hi at c_base + s*2*C_BYTES, lo right after
-    uint64_t *bars = reinterpret_cast<uint64_t *>(c_base + STAGES * 2 * C_BYTES);
-    uint64_t *full = bars, *empty = bars + STAGES, *s_full = bars + 2 * STAGES, *e_ready = s_full + 2;
-    uint64_t *r_full = e_ready + 2, *o_full = r_full + 1;
+    uint8_t *ring1 = smem + 2 * R_BYTES;                // stage s: C tile row-major, hi then lo (GEMM1's B, K-major)
+    uint8_t *ring2 = ring1 + STAGES * 2 * C_BYTES;      // stage s: C^T tile, hi then lo          (GEMM2's B, K-major)
+    uint64_t *bars = reinterpret_cast<uint64_t *>(ring2 + STAGES * 2 * T_BYTES);
+    uint64_t *full1 = bars, *empty1 = full1 + STAGES, *full2 = empty1 + STAGES, *empty2 = full2 + STAGES;
+    uint64_t *s_full = empty2 + STAGES, *e_ready = s_full + 2, *se_free = e_ready + 2, *r_full = se_free + 2, *o_full = r_full + 1;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(o_full + 1);
+    float *rowsum_x = reinterpret_cast<float *>(tmem_slot + 4);     // [128] partial row sums of warpgroup 1
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int rt = blockIdx.x / n_split, sp = blockIdx.x % n_split;
@@ -149,13 +237,18 @@ softmax_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_r_hi, const __gri
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_r_lo));
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_c_hi));
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_c_lo));
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_ct_hi));
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_ct_lo));
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(&full[s], 1);
-            mbar_init(&empty[s], 1);
+            mbar_init(&full1[s], 1);
+            mbar_init(&empty1[s], 1);
+            mbar_init(&full2[s], 1);
+            mbar_init(&empty2[s], 1);
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&s_full[b], 1);
             mbar_init(&e_ready[b], 128);
+            mbar_init(&se_free[b], 1);
         }
         mbar_init(r_full, 1);
         mbar_init(o_full, 1);
@@ -171,7 +264,7 @@ softmax_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_r_hi, const __gri
     const uint32_t tmem = *tmem_slot;
 
     if (warp == 0 && lane == 0) {
-        // ===================== TMA producer =====================
+        // ===================== TMA producer, ring 1: R tile once, then the row-major C tiles =====================
         mbar_expect_tx(r_full, 2 * R_BYTES);
         for (int c = 0; c < KCH; ++c) {
             tma_load_2d(r_hi + c * R_CHUNK, &map_r_hi, c * 32, row0, r_full);
@@ -179,101 +272,104 @@ softmax_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_r_hi, const __gri
         }
         for (int i = 0; i < n_tiles; ++i) {
             const int s = i % STAGES;
-            mbar_wait(&empty[s], ((i / STAGES) & 1) ^ 1);
-            uint8_t *hi = c_base + s * 2 * C_BYTES, *lo = hi + C_BYTES;
-            mbar_expect_tx(&full[s], 2 * C_BYTES);
+            mbar_wait(&empty1[s], ((i / STAGES) & 1) ^ 1);
+            uint8_t *hi = ring1 + s * 2 * C_BYTES, *lo = hi + C_BYTES;
+            mbar_expect_tx(&full1[s], 2 * C_BYTES);
             for (int c = 0; c < KCH; ++c) {
-                tma_load_2d(hi + c * C_CHUNK, &map_c_hi, c * 32, (t0 + i) * BN, &full[s]);
-                tma_load_2d(lo + c * C_CHUNK, &map_c_lo, c * 32, (t0 + i) * BN, &full[s]);
+                tma_load_2d(hi + c * C_CHUNK, &map_c_hi, c * 32, (t0 + i) * BN, &full1[s]);
+                tma_load_2d(lo + c * C_CHUNK, &map_c_lo, c * 32, (t0 + i) * BN, &full1[s]);
             }
         }
-    } else if (warp == 1 && lane == 0) {
-        // ===================== MMA issuer =====================
-        constexpr uint32_t idesc1 = instr_desc(BM, BN, 0);      // S[128 x 64]  = R (K-major)  x C (K-major)
-        constexpr uint32_t idesc2 = instr_desc(BM, D, 1);       // O[128 x D ] += E (TMEM)     x C (MN-major)
-        const uint32_t r_hi_a = smem_u32(r_hi), r_lo_a = smem_u32(r_lo);
-        auto gemm2 = [&](int j) {
-            const int s = j % STAGES, b = j & 1;
-            const uint32_t c_hi_a = smem_u32(c_base + s * 2 * C_BYTES), c_lo_a = c_hi_a + C_BYTES;
-            const uint32_t e_hi = tmem + COL_SE + b * BN, e_lo = tmem + COL_ELO + b * BN;
-#pragma unroll
-            for (int part = 0; part < 3; ++part) {
-                const uint32_t ea = (part == 1) ? e_lo : e_hi;
-                const uint32_t cb = (part == 2) ? c_lo_a : c_hi_a;
-#pragma unroll
-                for (int ks = 0; ks < BN / 8; ++ks) {
-                    // B: 8 rows (K) x D floats (N, contiguous): MN-major, 128-byte chunks C_CHUNK apart
-                    const uint64_t bd = smem_desc(cb + ks * 1024, C_CHUNK, 1024);
-                    mma_ts(tmem + COL_O, ea + ks * 8, bd, idesc2, (j > 0 || part > 0 || ks > 0) ? 1u : 0u);
-                }
+    } else if (warp == 2 && lane == 0) {
+        // ===================== TMA producer, ring 2: the transposed C tiles [d, 64] =====================
+        for (int i = 0; i < n_tiles; ++i) {
+            const int s = i % STAGES;
+            mbar_wait(&empty2[s], ((i / STAGES) & 1) ^ 1);
+            uint8_t *hi = ring2 + s * 2 * T_BYTES, *lo = hi + T_BYTES;
+            mbar_expect_tx(&full2[s], 2 * T_BYTES);
+            for (int c = 0; c < JCH; ++c) {
+                tma_load_2d(hi + c * T_CHUNK, &map_ct_hi, (t0 + i) * BN + c * 32, 0, &full2[s]);
+                tma_load_2d(lo + c * T_CHUNK, &map_ct_lo, (t0 + i) * BN + c * 32, 0, &full2[s]);
             }
-            tc_commit(&empty[s]);                               // stage free once GEMM2 has read it
-        };
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer 1: S = R C^T (three tf32 products, small ones first) =====================
+        constexpr uint32_t idesc1 = instr_desc(BM, BN, 0);      // S[128 x 64] = R (K-major, K = d) x C (K-major)
+        const uint32_t r_hi_a = smem_u32(r_hi), r_lo_a = smem_u32(r_lo);
         mbar_wait(r_full, 0);
         for (int i = 0; i < n_tiles; ++i) {
             const int s = i % STAGES, b = i & 1;
-            mbar_wait(&full[s], (i / STAGES) & 1);
+            mbar_wait(&full1[s], (i / STAGES) & 1);
+            mbar_wait(&se_free[b], ((i >> 1) & 1) ^ 1);          // GEMM2 of tile i-2 has finished reading E from this buffer
             tc_fence_after();
-            const uint32_t c_hi_a = smem_u32(c_base + s * 2 * C_BYTES), c_lo_a = c_hi_a + C_BYTES;
+            const uint32_t c_hi_a = smem_u32(ring1 + s * 2 * C_BYTES), c_lo_a = c_hi_a + C_BYTES;
 #pragma unroll
             for (int part = 0; part < 3; ++part) {
-                const uint32_t ra = (part == 1) ? r_lo_a : r_hi_a;
-                const uint32_t cb = (part == 2) ? c_lo_a : c_hi_a;
+                const uint32_t ra = (part == 0) ? r_lo_a : r_hi_a;
+                const uint32_t cb = (part == 1) ? c_lo_a : c_hi_a;
 #pragma unroll
                 for (int c = 0; c < KCH; ++c)
-#pragma unroll
-                    for (int ks = 0; ks < 4; ++ks) {
-                        const uint64_t ad = smem_desc(ra + c * R_CHUNK + ks * 32, 16, 1024);
-                        const uint64_t bd = smem_desc(cb + c * C_CHUNK + ks * 32, 16, 1024);
-                        mma_ss(tmem + COL_SE + b * BN, ad, bd, idesc1, (part > 0 || c > 0 || ks > 0) ? 1u : 0u);
-                    }
+                    if (elect_one())
+                        mma_ss_x4(tmem + COL_SE + b * BN, smem_desc(ra + c * R_CHUNK, 16, 1024), smem_desc(cb + c * C_CHUNK, 16, 1024), idesc1,
+                                  (part > 0 || c > 0) ? 1u : 0u);
             }
-            tc_commit(&s_full[b]);
-            if (i > 0) {
-                mbar_wait(&e_ready[(i - 1) & 1], ((i - 1) >> 1) & 1);
-                tc_fence_after();
-                gemm2(i - 1);
+            if (elect_one()) {
+                tc_commit(&s_full[b]);
+                tc_commit(&empty1[s]);                          // GEMM1 was the only reader of this stage
             }
+            __syncwarp();
         }
-        if (n_tiles > 0) {
-            const int j = n_tiles - 1;
-            mbar_wait(&e_ready[j & 1], (j >> 1) & 1);
+    } else if (warp == 3) {
+        // ===================== MMA issuer 2: O += E C  (A = E from TMEM, B = C^T tile) =====================
+        constexpr uint32_t idesc2 = instr_desc(BM, D, 0);       // O[128 x d] += E (TMEM, K = 64) x C^T (K-major)
+        for (int j = 0; j < n_tiles; ++j) {
+            const int s = j % STAGES, b = j & 1;
+            mbar_wait(&e_ready[b], (j >> 1) & 1);
+            mbar_wait(&full2[s], (j / STAGES) & 1);
             tc_fence_after();
-            gemm2(j);
+            const uint32_t t_hi_a = smem_u32(ring2 + s * 2 * T_BYTES), t_lo_a = t_hi_a + T_BYTES;
+            const uint32_t e_hi = tmem + COL_SE + b * BN, e_lo = tmem + COL_ELO + b * BN;
+            // the two correction products go to their own accumulator: the tensor core rounds its fp32
+            // accumulations toward zero, so the long hi*hi sum must not also carry them
+#pragma unroll
+            for (int part = 0; part < 3; ++part) {
+                const uint32_t ea = (part == 0) ? e_lo : e_hi;
+                const uint32_t tb = (part == 1) ? t_lo_a : t_hi_a;
+                const uint32_t od = tmem + ((part == 2) ? COL_O : COL_OC);
+#pragma unroll
+                for (int c = 0; c < JCH; ++c) {
+                    const bool first = (part == 2) ? (c == 0) : (part == 0 && c == 0);
+                    if (elect_one()) mma_ts_x4(od, ea + c * 32, smem_desc(tb + c * T_CHUNK, 16, 1024), idesc2, (j > 0 || !first) ? 1u : 0u);
+                }
+            }
+            if (elect_one()) {
+                tc_commit(&empty2[s]);
+                tc_commit(&se_free[b]);
+            }
+            __syncwarp();
         }
-        tc_commit(o_full);
+        if (elect_one()) tc_commit(o_full);
+        __syncwarp();
     } else if (warp >= 4) {
-        // ===================== epilogue: thread = TMEM lane = row =====================
+        // ===== epilogue: two warpgroups ping-pong over the tiles (warpgroup w owns tiles of parity w and the
+        // ===== TMEM buffers of parity w); thread = TMEM lane = row
+        const int wg = (warp - 4) >> 2;
         const int q = warp & 3;
         const int row = q * 32 + lane;
         const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
         float rowsum = 0.f;
-        for (int i = 0; i < n_tiles; ++i) {
-            const int b = i & 1;
+        for (int i = wg; i < n_tiles; i += 2) {
+            const int b = wg;
             mbar_wait(&s_full[b], (i >> 1) & 1);
             tc_fence_after();
             const int64_t col0 = (int64_t)(t0 + i) * BN;
+            const bool full_tile = col0 + BN <= n_c;
 #pragma unroll
             for (int h = 0; h < BN / 32; ++h) {
                 uint32_t v[32], lo[32];
                 tmem_ld32(lane_base + COL_SE + b * BN + h * 32, v);
-#pragma unroll
-                for (int k = 0; k < 32; k += 4) {
-                    float cs[4] = {1.f, 1.f, 1.f, 1.f};
-                    if (colscale != nullptr) {
-                        const float4 c4 = __ldg(reinterpret_cast<const float4 *>(colscale + col0 + h * 32 + k));
-                        cs[0] = c4.x; cs[1] = c4.y; cs[2] = c4.z; cs[3] = c4.w;
-                    }
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const bool valid = col0 + h * 32 + k + u < n_c;
-                        const float e = valid ? ex2(__uint_as_float(v[k + u]) - offset) * cs[u] : 0.f;
-                        rowsum += e;
-                        const uint32_t hi = __float_as_uint(e) & 0xffffe000u;      // tf32(e), truncated
-                        v[k + u] = hi;
-                        lo[k + u] = __float_as_uint(e - __uint_as_float(hi));
-                    }
-                }
+                if (full_tile) exp_chunk<false>(v, lo, offset, colscale, col0 + h * 32, n_c, rowsum);
+                else exp_chunk<true>(v, lo, offset, colscale, col0 + h * 32, n_c, rowsum);
                 tmem_st32(lane_base + COL_SE + b * BN + h * 32, v);                 // E_hi over S, in place
                 tmem_st32(lane_base + COL_ELO + b * BN + h * 32, lo);
             }
@@ -281,27 +377,35 @@ softmax_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_r_hi, const __gri
             tc_fence_before();
             mbar_arrive(&e_ready[b]);
         }
-        // ---- O and the row sums: once per CTA ----
-        mbar_wait(o_full, 0);
-        tc_fence_after();
-        const int64_t grow = (int64_t)row0 + row;
-        if (n_tiles > 0) {
+        // ---- combine the two warpgroups' row sums; warpgroup 0 reads O out of TMEM once per CTA ----
+        if (wg == 1) rowsum_x[row] = rowsum;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (wg == 0) {
+            rowsum += rowsum_x[row];
+            mbar_wait(o_full, 0);
+            tc_fence_after();
+            const int64_t grow = (int64_t)row0 + row;
+            if (n_tiles > 0) {
 #pragma unroll
-            for (int h = 0; h < D / 32; ++h) {
-                uint32_t v[32];
-                tmem_ld32(lane_base + COL_O + h * 32, v);
-                if (grow < n_r) {
-                    float4 *dst = reinterpret_cast<float4 *>(o_part + ((size_t)sp * n_r + grow) * D + h * 32);
+                for (int h = 0; h < D / 32; ++h) {
+                    uint32_t v[32], c[32];
+                    tmem_ld32(lane_base + COL_O + h * 32, v);
+                    tmem_ld32(lane_base + COL_OC + h * 32, c);
+                    if (grow < n_r) {
+                        float4 *dst = reinterpret_cast<float4 *>(o_part + ((size_t)sp * n_r + grow) * D + h * 32);
 #pragma unroll
-                    for (int k = 0; k < 8; ++k)
-                        dst[k] = make_float4(__uint_as_float(v[4 * k]), __uint_as_float(v[4 * k + 1]), __uint_as_float(v[4 * k + 2]),
-                                             __uint_as_float(v[4 * k + 3]));
+                        for (int k = 0; k < 8; ++k)
+                            dst[k] = make_float4(__uint_as_float(v[4 * k]) + __uint_as_float(c[4 * k]),
+                                                 __uint_as_float(v[4 * k + 1]) + __uint_as_float(c[4 * k + 1]),
+                                                 __uint_as_float(v[4 * k + 2]) + __uint_as_float(c[4 * k + 2]),
+                                                 __uint_as_float(v[4 * k + 3]) + __uint_as_float(c[4 * k + 3]));
+                    }
                 }
+            } else if (grow < n_r) {
+                for (int k = 0; k < D; ++k) o_part[((size_t)sp * n_r + grow) * D + k] = 0.f;
             }
-        } else if (grow < n_r) {
-            for (int k = 0; k < D; ++k) o_part[((size_t)sp * n_r + grow) * D + k] = 0.f;
+            if (grow < n_r && rowsum_part != nullptr) rowsum_part[(size_t)sp * n_r + grow] = rowsum;
         }
-        if (grow < n_r && rowsum_part != nullptr) rowsum_part[(size_t)sp * n_r + grow] = rowsum;
     }
 
     tc_fence_before();
@@ -328,15 +432,16 @@ EncodeTiledFn encode_fn() {
     return fn;
 }
 
-// [rows, dim] fp32 row-major -> boxes of 32 floats (128 B, SWIZZLE_128B) x box_rows rows; rows beyond n read as 0
-int make_map(CUtensorMap *map, const float *base, int64_t rows, int dim, int box_rows) {
+// [rows, cols] fp32, row pitch ``pitch`` floats -> boxes of 32 floats (128 B, SWIZZLE_128B) x box_rows rows;
+// out-of-range rows / columns read as 0
+int make_map(CUtensorMap *map, const float *base, int64_t rows, int64_t cols, int64_t pitch, int box_rows) {
     EncodeTiledFn fn = encode_fn();
     if (fn == nullptr) {
         ssl::set_error("cuTensorMapEncodeTiled is not available from this driver");
         return SSL_E_CUDA;
     }
-    cuuint64_t gdim[2] = {(cuuint64_t)dim, (cuuint64_t)rows};
-    cuuint64_t gstride[1] = {(cuuint64_t)dim * sizeof(float)};
+    cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)pitch * sizeof(float)};
     cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1u, 1u};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), gdim, gstride, box, estr,
@@ -350,24 +455,28 @@ int make_map(CUtensorMap *map, const float *base, int64_t rows, int dim, int box
 }
 
 template <int D>
-int launch_tc(const float *R_hi, const float *R_lo, int64_t n_r, const float *C_hi, const float *C_lo, int64_t n_c,
-              const float *colscale, float offset, int n_split, float *rowsum_part, float *o_part, cudaStream_t st) {
-    CUtensorMap mr_hi, mr_lo, mc_hi, mc_lo;
+int launch_tc(const float *R_hi, const float *R_lo, int64_t n_r, const float *C_hi, const float *C_lo, const float *CT_hi,
+              const float *CT_lo, int64_t ct_pitch, int64_t n_c, const float *colscale, float offset, int n_split,
+              float *rowsum_part, float *o_part, cudaStream_t st) {
+    CUtensorMap mr_hi, mr_lo, mc_hi, mc_lo, mt_hi, mt_lo;
     int rc;
-    if ((rc = make_map(&mr_hi, R_hi, n_r, D, BM)) != SSL_OK) return rc;
-    if ((rc = make_map(&mr_lo, R_lo, n_r, D, BM)) != SSL_OK) return rc;
-    if ((rc = make_map(&mc_hi, C_hi, n_c, D, BN)) != SSL_OK) return rc;
-    if ((rc = make_map(&mc_lo, C_lo, n_c, D, BN)) != SSL_OK) return rc;
+    if ((rc = make_map(&mr_hi, R_hi, n_r, D, D, BM)) != SSL_OK) return rc;
+    if ((rc = make_map(&mr_lo, R_lo, n_r, D, D, BM)) != SSL_OK) return rc;
+    if ((rc = make_map(&mc_hi, C_hi, n_c, D, D, BN)) != SSL_OK) return rc;
+    if ((rc = make_map(&mc_lo, C_lo, n_c, D, D, BN)) != SSL_OK) return rc;
+    if ((rc = make_map(&mt_hi, CT_hi, D, n_c, ct_pitch, D)) != SSL_OK) return rc;
+    if ((rc = make_map(&mt_lo, CT_lo, D, n_c, ct_pitch, D)) != SSL_OK) return rc;
     constexpr int KCH = D / 32;
-    const size_t smem = 1024 + 2 * (size_t)KCH * BM * 128 + (size_t)STAGES * 2 * KCH * BN * 128 + 16 * sizeof(uint64_t);
+    const size_t smem = 1024 + 2 * (size_t)KCH * BM * 128 + (size_t)STAGES * 2 * KCH * BN * 128 + (size_t)STAGES * 2 * (BN / 32) * D * 128 +
+                        32 * sizeof(uint64_t) + 16 + 128 * sizeof(float);
     static bool configured = false;
     if (!configured) {
         SSL_CUDA(cudaFuncSetAttribute(softmax_gemm_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
     const int64_t grid = ((n_r + BM - 1) / BM) * n_split;
-    softmax_gemm_tc_kernel<D><<<(unsigned)grid, kNumThreads, smem, st>>>(mr_hi, mr_lo, mc_hi, mc_lo, n_r, n_c, colscale, offset, n_split,
-                                                                         rowsum_part, o_part);
+    softmax_gemm_tc_kernel<D><<<(unsigned)grid, kNumThreads, smem, st>>>(mr_hi, mr_lo, mc_hi, mc_lo, mt_hi, mt_lo, n_r, n_c, colscale, offset,
+                                                                         n_split, rowsum_part, o_part);
     SSL_LAUNCH_CHECK("softmax_gemm_tc_kernel");
     return SSL_OK;
 }
@@ -375,16 +484,19 @@ int launch_tc(const float *R_hi, const float *R_lo, int64_t n_r, const float *C_
 }  // namespace
 
 extern "C" int ssl_softmax_gemm_tf32x3(const float *R_hi, const float *R_lo, int64_t n_r, const float *C_hi, const float *C_lo,
-                                       int64_t n_c, int32_t dim, const float *colscale, float offset, int32_t n_split,
-                                       float *rowsum_part, float *o_part, void *stream) {
-    SSL_CHECK_ARG(R_hi && R_lo && C_hi && C_lo && o_part, "ssl_softmax_gemm_tf32x3: null argument");
+                                       const float *CT_hi, const float *CT_lo, int64_t ct_pitch, int64_t n_c, int32_t dim,
+                                       const float *colscale, float offset, int32_t n_split, float *rowsum_part, float *o_part,
+                                       void *stream) {
+    SSL_CHECK_ARG(R_hi && R_lo && C_hi && C_lo && CT_hi && CT_lo && o_part, "ssl_softmax_gemm_tf32x3: null argument");
+    SSL_CHECK_ARG(ct_pitch >= n_c && ct_pitch % 4 == 0, "ssl_softmax_gemm_tf32x3: ct_pitch must be >= n_c and a multiple of 4");
     SSL_CHECK_ARG(dim == 32 || dim == 64, "ssl_softmax_gemm_tf32x3: dim %d not supported (32 or 64; other sizes use ssl_softmax_gemm)", dim);
     SSL_CHECK_ARG((n_split >= 1 && n_split <= (n_c + BN - 1) / BN) || n_c == 0, "ssl_softmax_gemm_tf32x3: n_split %d exceeds the number of C tiles", n_split);
     SSL_CHECK_ARG(((reinterpret_cast<uintptr_t>(R_hi) | reinterpret_cast<uintptr_t>(R_lo) | reinterpret_cast<uintptr_t>(C_hi) |
-                    reinterpret_cast<uintptr_t>(C_lo) | reinterpret_cast<uintptr_t>(o_part)) & 15) == 0,
+                    reinterpret_cast<uintptr_t>(C_lo) | reinterpret_cast<uintptr_t>(CT_hi) | reinterpret_cast<uintptr_t>(CT_lo) |
+                    reinterpret_cast<uintptr_t>(o_part)) & 15) == 0,
                   "ssl_softmax_gemm_tf32x3: operands must be 16-byte aligned");
     if (n_r == 0 || n_c == 0) return SSL_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    if (dim == 32) return launch_tc<32>(R_hi, R_lo, n_r, C_hi, C_lo, n_c, colscale, offset, n_split, rowsum_part, o_part, st);
-    return launch_tc<64>(R_hi, R_lo, n_r, C_hi, C_lo, n_c, colscale, offset, n_split, rowsum_part, o_part, st);
+    if (dim == 32) return launch_tc<32>(R_hi, R_lo, n_r, C_hi, C_lo, CT_hi, CT_lo, ct_pitch, n_c, colscale, offset, n_split, rowsum_part, o_part, st);
+    return launch_tc<64>(R_hi, R_lo, n_r, C_hi, C_lo, CT_hi, CT_lo, ct_pitch, n_c, colscale, offset, n_split, rowsum_part, o_part, st);
 }

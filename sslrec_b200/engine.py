@@ -604,11 +604,11 @@ def _nce_fwd(e1: Rows, e2: Rows, table: Rows, idx, idx2, tau, norm_mode, mean, d
     t_hat, rinv_t = torch.empty(npad, d, **f), torch.empty(max(n, 1), **f)
     if use_tc:
         a_t = t_t = None
-        a_hi, a_lo = torch.empty(Bp, d, **f), torch.empty(Bp, d, **f)
-        t_hi, t_lo = torch.empty(npad, d, **f), torch.empty(npad, d, **f)
+        a_hi, a_lo, a_thi, a_tlo = torch.empty(Bp, d, **f), torch.empty(Bp, d, **f), torch.empty(d, Bp, **f), torch.empty(d, Bp, **f)
+        t_hi, t_lo, t_thi, t_tlo = torch.empty(npad, d, **f), torch.empty(npad, d, **f), torch.empty(d, npad, **f), torch.empty(d, npad, **f)
     else:
         t_t = torch.empty(npad // 64, d, 64, **f)
-        a_hi = a_lo = t_hi = t_lo = None
+        a_hi = a_lo = t_hi = t_lo = a_thi = a_tlo = t_thi = t_tlo = None
     n_split = choose_split((B + 127) // 128, npad // 64, slots=148 if use_tc else 296)
     rs_part, o_part = torch.zeros(n_split, B, **f), torch.zeros(n_split, B, d, **f)
     rowsum, obar, loss_b, out = torch.empty(B, **f), torch.empty(B, d, **f), torch.empty(B, **f), torch.empty((), **f)
@@ -616,15 +616,18 @@ def _nce_fwd(e1: Rows, e2: Rows, table: Rows, idx, idx2, tau, norm_mode, mean, d
     with torch.cuda.device(dev):
         s = _stream(table.base)
         check(lib.ssl_rows_normalize(e1.ptr, e1.stride, idx.data_ptr(), B, d, norm_mode, off, a_hat.data_ptr(),
-                                     _ptr(a_t), rinv1.data_ptr(), _ptr(a_hi), _ptr(a_lo), s), 'ssl_rows_normalize(e1)')
+                                     _ptr(a_t), rinv1.data_ptr(), _ptr(a_hi), _ptr(a_lo), _ptr(a_thi), _ptr(a_tlo), Bp, s),
+              'ssl_rows_normalize(e1)')
         check(lib.ssl_rows_normalize(e2.ptr, e2.stride, idx2.data_ptr(), B, d, norm_mode, 1.0, p_hat.data_ptr(), None,
-                                     rinv2.data_ptr(), None, None, s), 'ssl_rows_normalize(e2)')
+                                     rinv2.data_ptr(), None, None, None, None, 0, s), 'ssl_rows_normalize(e2)')
         check(lib.ssl_rows_normalize(table.ptr, table.stride, None, n, d, norm_mode, 1.0, t_hat.data_ptr(),
-                                     _ptr(t_t), rinv_t.data_ptr(), _ptr(t_hi), _ptr(t_lo), s), 'ssl_rows_normalize(table)')
+                                     _ptr(t_t), rinv_t.data_ptr(), _ptr(t_hi), _ptr(t_lo), _ptr(t_thi), _ptr(t_tlo), npad, s),
+              'ssl_rows_normalize(table)')
         with _timed('nce_gemm_fwd', dict(B=B, n=n, dim=d, tc=use_tc)):
             if use_tc:
-                check(lib.ssl_softmax_gemm_tf32x3(a_hi.data_ptr(), a_lo.data_ptr(), B, t_hi.data_ptr(), t_lo.data_ptr(), n, d, None, off,
-                                                  n_split, rs_part.data_ptr(), o_part.data_ptr(), s), 'ssl_softmax_gemm_tf32x3(fwd)')
+                check(lib.ssl_softmax_gemm_tf32x3(a_hi.data_ptr(), a_lo.data_ptr(), B, t_hi.data_ptr(), t_lo.data_ptr(), t_thi.data_ptr(),
+                                                  t_tlo.data_ptr(), npad, n, d, None, off, n_split, rs_part.data_ptr(), o_part.data_ptr(), s),
+                      'ssl_softmax_gemm_tf32x3(fwd)')
             else:
                 check(lib.ssl_softmax_gemm(a_hat.data_ptr(), B, t_hat.data_ptr(), t_t.data_ptr(), n, d, None, off, n_split,
                                            rs_part.data_ptr(), o_part.data_ptr(), s), 'ssl_softmax_gemm(fwd)')
@@ -637,7 +640,7 @@ def _nce_fwd(e1: Rows, e2: Rows, table: Rows, idx, idx2, tau, norm_mode, mean, d
                                    loss_b.data_ptr(), s), 'ssl_nce_finalize')
         check(lib.ssl_sum(loss_b.data_ptr(), B, (1.0 / B) if mean else 1.0, out.data_ptr(), s), 'ssl_sum')
     saved = (e1, e2, table, idx, tau, mean, a_hat, a_t, p_hat, rinv1, rinv2, t_hat, rinv_t, rowsum, obar, full_table, comm,
-             (a_hi, a_lo, t_hi, t_lo) if use_tc else None)
+             (a_hi, a_lo, a_thi, a_tlo, t_hi, t_lo) if use_tc else None)
     return out, saved
 
 
@@ -667,10 +670,11 @@ def _nce_bwd(saved, g):
             dt_part = torch.empty(n_split, n, d, **f)
             with _timed('nce_gemm_bwd', dict(B=B, n=n, dim=d, tc=bool(tc))):
                 if tc:
-                    a_hi, a_lo, t_hi, t_lo = tc
-                    check(lib.ssl_softmax_gemm_tf32x3(t_hi.data_ptr(), t_lo.data_ptr(), n, a_hi.data_ptr(), a_lo.data_ptr(), B, d,
-                                                      colscale.data_ptr(), LOG2E / tau, n_split, None, dt_part.data_ptr(), s),
-                          'ssl_softmax_gemm_tf32x3(bwd)')
+                    a_hi, a_lo, a_thi, a_tlo, t_hi, t_lo = tc
+                    Bp = a_thi.shape[1]
+                    check(lib.ssl_softmax_gemm_tf32x3(t_hi.data_ptr(), t_lo.data_ptr(), n, a_hi.data_ptr(), a_lo.data_ptr(), a_thi.data_ptr(),
+                                                      a_tlo.data_ptr(), Bp, B, d, colscale.data_ptr(), LOG2E / tau, n_split, None,
+                                                      dt_part.data_ptr(), s), 'ssl_softmax_gemm_tf32x3(bwd)')
                 else:
                     check(lib.ssl_softmax_gemm(t_hat.data_ptr(), n, a_hat.data_ptr(), a_t.data_ptr(), B, d, colscale.data_ptr(),
                                                LOG2E / tau, n_split, None, dt_part.data_ptr(), s), 'ssl_softmax_gemm(bwd)')

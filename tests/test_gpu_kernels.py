@@ -161,8 +161,12 @@ def test_infonce_term_forward_backward(dim, B, n, use_tc, monkeypatch):
     ref = O.infonce_loss_sum(*ref_in, tau)
     ref.backward()
     assert abs(loss.item() - ref.item()) <= 2e-6 * abs(ref.item())
+    # absolute term relative to the largest gradient entry: 2e-6 for the FP32-FMA kernel; 1e-5 for the tcgen05
+    # 3xTF32 kernel, whose tensor-core accumulators round toward zero over up to ~10^3 accumulations per output
+    # (measured 0.5-2.5e-6 of the largest entry, tools/debug_tc.py)
+    rel_atol = 1e-5 if (use_tc and dim in (32, 64)) else 2e-6
     for a, b, name in zip(ins, ref_in, ('e1', 'e2', 'table')):
-        H.close(a.grad, b.grad, 2e-4, 2e-6 * b.grad.abs().max().item(), 'grad ' + name)
+        H.close(a.grad, b.grad, 2e-4, rel_atol * b.grad.abs().max().item(), 'grad ' + name)
 
 
 def test_spec_nodes_infonce_and_bpr_dense():
@@ -226,5 +230,5 @@ def test_c_abi_rejects_bad_arguments():
     rc = _lib.lib.ssl_sumsq(None, 4, None, None)
     assert rc == -1 and b'null' in _lib.lib.ssl_last_error()
     x = torch.zeros(8, device='cuda')
-    rc = _lib.lib.ssl_rows_normalize(x.data_ptr(), 6, None, 1, 6, 0, 1.0, x.data_ptr(), None, None, None)
+    rc = _lib.lib.ssl_rows_normalize(x.data_ptr(), 6, None, 1, 6, 0, 1.0, x.data_ptr(), None, None, None, None, None, None, 0, None)
     assert rc == -1                                               # dim must be a multiple of 4
