@@ -334,19 +334,28 @@ def run_ours(args):
                 'launches_per_step': len(prop) / K, 'share_of_step': prop_ms / K / prof_ms if prof_ms else None,
                 'note': 'the 41 MB/view tables of this graph fit the 126 MB L2, so achieved counts L2 hits and can exceed the HBM peak; '
                         'traffic (ncu dram bytes) is in profiles/'}
-    # the dense InfoNCE contraction, reported separately against the FP32 FMA pipe (not HBM-bound)
-    nce_ms = sum(summ[k]['ms'] for k in ('nce_gemm_fwd', 'nce_gemm_bwd') if k in summ)
-    terms = {'simgcl': [n_user, n_item], 'sgl': [n_user, n_item, n_item]}.get(model_name, [])
-    nce_flops_step = sum(8.0 * BATCH * n * d for n in terms)          # fwd 4 B N d + bwd 4 B N d per term
+    # the dense InfoNCE contraction (not HBM-bound): on the tcgen05 tensor cores with 3xTF32 error compensation when
+    # dim is 32 / 64, else on the FP32 FMA pipe
+    nce = [(m, ms) for name, m, ms in launches_all if name in ('nce_gemm_fwd', 'nce_gemm_bwd')]
+    nce_ms = sum(ms for _, ms in nce)
+    nce_flops_step = sum(4.0 * m['B'] * m['n'] * m['dim'] for m, _ in nce) / K          # fp32-equivalent: S = R C^T and O += E C
     sm_mhz = (clocks or {}).get('sm_mhz') or 1965.0
-    fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
     roofline_nce = None
-    if nce_ms:
-        tf = nce_flops_step * K / (nce_ms * 1e-3) / 1e12
-        roofline_nce = {'kernel': 'softmax_gemm_kernel (ssl_softmax_gemm, fwd+bwd)', 'bound': 'fp32_fma', 'achieved': tf,
-                        'peak': fp32_peak, 'peak_kind': f'148 SM x 128 FMA/clk x 2 x {sm_mhz:.0f} MHz (median SM clock under load)',
-                        'unit': 'TFLOP/s', 'frac': tf / fp32_peak, 'flop_per_step': nce_flops_step,
-                        'share_of_step': nce_ms / K / prof_ms}
+    if nce:
+        used_tc = all(m.get('tc') for m, _ in nce)
+        eq_tf = nce_flops_step * K / (nce_ms * 1e-3) / 1e12
+        if used_tc:
+            peak = peaks['bf16_tflops'] / 2.0
+            roofline_nce = {'kernel': 'softmax_gemm_tc_kernel (ssl_softmax_gemm_tf32x3, forward + backward launches)', 'bound': 'tensor',
+                            'achieved': 3.0 * eq_tf, 'peak': peak, 'unit': 'TFLOP/s', 'frac': 3.0 * eq_tf / peak,
+                            'peak_kind': peak_kind + ' cuBLAS bf16 burst / 2 (kind::tf32 issues at half the bf16 rate)',
+                            'fp32_equivalent_tflops': eq_tf, 'mma_flop_per_step': 3.0 * nce_flops_step,
+                            'note': 'three tf32 products per fp32-grade product (3xTF32)', 'share_of_step': nce_ms / K / prof_ms}
+        else:
+            fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
+            roofline_nce = {'kernel': 'softmax_gemm_kernel (ssl_softmax_gemm, forward + backward launches)', 'bound': 'fp32_fma', 'achieved': eq_tf,
+                            'peak': fp32_peak, 'peak_kind': f'148 SM x 128 FMA/clk x 2 x {sm_mhz:.0f} MHz', 'unit': 'TFLOP/s',
+                            'frac': eq_tf / fp32_peak, 'flop_per_step': nce_flops_step, 'share_of_step': nce_ms / K / prof_ms}
     emb_per_step = 2.0 * views * L * nnz if model_name != 'sgl' else 2.0 * L * nnz * (1 + 2 * hp['keep_rate'])
 
     # ---- CPU baseline on this box's host cores (bounded sample) ----

@@ -22,12 +22,12 @@
 //   warp 3 / lane 0 : MMA issuer 2.  GEMM2 (M=128, N=d, K=64): A = E read from TENSOR MEMORY, B = C^T tile ->
 //                     O in TMEM, accumulated over all tiles.  Two issuing threads because tf32 MMAs are only
 //                     K = 8 deep: one thread cannot issue them as fast as the tensor pipe retires them.
-//   warps 4-7, 8-11 : two epilogue warpgroups ping-ponging over the tiles (parity), thread = TMEM lane =
-//                     row.  tcgen05.ld S, ex2, row sums in registers (no cross-thread reduction), split E
-//                     into hi / lo, tcgen05.st them back into TMEM (E_hi over S in place); finally O is
-//                     read out of TMEM once per CTA.
-//   TMEM columns    : [0,128) S/E_hi x2 buffers, [128,256) E_lo x2 buffers, [256,256+d) O (hi*hi),
-//                     [384,384+d) O correction terms.
+//   warps 4-11,12-19: two epilogue groups (256 threads each) ping-ponging over the tiles (parity); thread =
+//                     (TMEM lane = row, one 32-column half of the tile).  tcgen05.ld S (which frees the S
+//                     buffer for the next GEMM1 at once), ex2, row sums in registers, tf32 split of E,
+//                     tcgen05.st E_hi / E_lo into their own TMEM buffers; finally O is read out once per CTA.
+//   TMEM columns    : [0,128) S x2, [128,256) E_hi x2, [256,384) E_lo x2, [384,384+d) O (hi*hi),
+//                     [448,448+d) O correction terms -- all 512 columns.
 #include <cuda.h>
 #include <cstdlib>
 
@@ -36,9 +36,9 @@
 namespace {
 
 constexpr int BM = 128, BN = 64, STAGES = 2;
-constexpr int kNumThreads = 384;       // warps 0-3: TMA x2, MMA, spare; warps 4-7 and 8-11: two epilogue warpgroups
+constexpr int kNumThreads = 640;       // warps 0-3: TMA, MMA1, TMA, MMA2; warps 4-11 and 12-19: two epilogue groups of 256 threads
 constexpr uint32_t kTmemCols = 512;
-constexpr uint32_t COL_SE = 0, COL_ELO = 128, COL_O = 256, COL_OC = 384;
+constexpr uint32_t COL_S = 0, COL_EHI = 128, COL_ELO = 256, COL_O = 384, COL_OC = 448;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -221,9 +221,9 @@ softmax_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_r_hi, const __gri
     uint8_t *ring2 = ring1 + STAGES * 2 * C_BYTES;      // stage s: C^T tile, hi then lo          (GEMM2's B, K-major)
     uint64_t *bars = reinterpret_cast<uint64_t *>(ring2 + STAGES * 2 * T_BYTES);
     uint64_t *full1 = bars, *empty1 = full1 + STAGES, *full2 = empty1 + STAGES, *empty2 = full2 + STAGES;
-    uint64_t *s_full = empty2 + STAGES, *e_ready = s_full + 2, *se_free = e_ready + 2, *r_full = se_free + 2, *o_full = r_full + 1;
+    uint64_t *s_full = empty2 + STAGES, *s_free = s_full + 2, *e_ready = s_free + 2, *e_free = e_ready + 2, *r_full = e_free + 2, *o_full = r_full + 1;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(o_full + 1);
-    float *rowsum_x = reinterpret_cast<float *>(tmem_slot + 4);     // [128] partial row sums of warpgroup 1
+    float *rowsum_x = reinterpret_cast<float *>(tmem_slot + 4);     // [3][128] partial row sums of the other epilogue sub-groups
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int rt = blockIdx.x / n_split, sp = blockIdx.x % n_split;
@@ -247,8 +247,9 @@ softmax_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_r_hi, const __gri
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&s_full[b], 1);
-            mbar_init(&e_ready[b], 128);
-            mbar_init(&se_free[b], 1);
+            mbar_init(&s_free[b], 256);
+            mbar_init(&e_ready[b], 256);
+            mbar_init(&e_free[b], 1);
         }
         mbar_init(r_full, 1);
         mbar_init(o_full, 1);
@@ -300,7 +301,7 @@ softmax_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_r_hi, const __gri
         for (int i = 0; i < n_tiles; ++i) {
             const int s = i % STAGES, b = i & 1;
             mbar_wait(&full1[s], (i / STAGES) & 1);
-            mbar_wait(&se_free[b], ((i >> 1) & 1) ^ 1);          // GEMM2 of tile i-2 has finished reading E from this buffer
+            mbar_wait(&s_free[b], ((i >> 1) & 1) ^ 1);           // the epilogue of tile i-2 has read S out of this buffer
             tc_fence_after();
             const uint32_t c_hi_a = smem_u32(ring1 + s * 2 * C_BYTES), c_lo_a = c_hi_a + C_BYTES;
 #pragma unroll
@@ -310,7 +311,7 @@ softmax_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_r_hi, const __gri
 #pragma unroll
                 for (int c = 0; c < KCH; ++c)
                     if (elect_one())
-                        mma_ss_x4(tmem + COL_SE + b * BN, smem_desc(ra + c * R_CHUNK, 16, 1024), smem_desc(cb + c * C_CHUNK, 16, 1024), idesc1,
+                        mma_ss_x4(tmem + COL_S + b * BN, smem_desc(ra + c * R_CHUNK, 16, 1024), smem_desc(cb + c * C_CHUNK, 16, 1024), idesc1,
                                   (part > 0 || c > 0) ? 1u : 0u);
             }
             if (elect_one()) {
@@ -328,7 +329,7 @@ softmax_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_r_hi, const __gri
             mbar_wait(&full2[s], (j / STAGES) & 1);
             tc_fence_after();
             const uint32_t t_hi_a = smem_u32(ring2 + s * 2 * T_BYTES), t_lo_a = t_hi_a + T_BYTES;
-            const uint32_t e_hi = tmem + COL_SE + b * BN, e_lo = tmem + COL_ELO + b * BN;
+            const uint32_t e_hi = tmem + COL_EHI + b * BN, e_lo = tmem + COL_ELO + b * BN;
             // the two correction products go to their own accumulator: the tensor core rounds its fp32
             // accumulations toward zero, so the long hi*hi sum must not also carry them
 #pragma unroll
@@ -344,55 +345,55 @@ softmax_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_r_hi, const __gri
             }
             if (elect_one()) {
                 tc_commit(&empty2[s]);
-                tc_commit(&se_free[b]);
+                tc_commit(&e_free[b]);
             }
             __syncwarp();
         }
         if (elect_one()) tc_commit(o_full);
         __syncwarp();
     } else if (warp >= 4) {
-        // ===== epilogue: two warpgroups ping-pong over the tiles (warpgroup w owns tiles of parity w and the
-        // ===== TMEM buffers of parity w); thread = TMEM lane = row
-        const int wg = (warp - 4) >> 2;
-        const int q = warp & 3;
+        // ===== epilogue: two groups of 8 warps ping-pong over the tiles (group g owns the tiles and TMEM buffers of
+        // ===== parity g); inside a group, thread = (TMEM lane = row, one 32-column half of the 64-column tile)
+        const int e = warp - 4;
+        const int g = e >> 3, half = (e >> 2) & 1, q = warp & 3;
         const int row = q * 32 + lane;
         const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
         float rowsum = 0.f;
-        for (int i = wg; i < n_tiles; i += 2) {
-            const int b = wg;
-            mbar_wait(&s_full[b], (i >> 1) & 1);
+        for (int i = g; i < n_tiles; i += 2) {
+            const int b = g;
+            const uint32_t par = (i >> 1) & 1;
+            mbar_wait(&s_full[b], par);
             tc_fence_after();
-            const int64_t col0 = (int64_t)(t0 + i) * BN;
-            const bool full_tile = col0 + BN <= n_c;
-#pragma unroll
-            for (int h = 0; h < BN / 32; ++h) {
-                uint32_t v[32], lo[32];
-                tmem_ld32(lane_base + COL_SE + b * BN + h * 32, v);
-                if (full_tile) exp_chunk<false>(v, lo, offset, colscale, col0 + h * 32, n_c, rowsum);
-                else exp_chunk<true>(v, lo, offset, colscale, col0 + h * 32, n_c, rowsum);
-                tmem_st32(lane_base + COL_SE + b * BN + h * 32, v);                 // E_hi over S, in place
-                tmem_st32(lane_base + COL_ELO + b * BN + h * 32, lo);
-            }
+            uint32_t v[32], lo[32];
+            tmem_ld32(lane_base + COL_S + b * BN + half * 32, v);
+            tc_fence_before();
+            mbar_arrive(&s_free[b]);                             // GEMM1 of tile i+2 may overwrite S now
+            const int64_t col = (int64_t)(t0 + i) * BN + half * 32;
+            if (col + 32 <= n_c) exp_chunk<false>(v, lo, offset, colscale, col, n_c, rowsum);
+            else exp_chunk<true>(v, lo, offset, colscale, col, n_c, rowsum);
+            mbar_wait(&e_free[b], par ^ 1);                      // GEMM2 of tile i-2 has consumed the previous E
+            tc_fence_after();
+            tmem_st32(lane_base + COL_EHI + b * BN + half * 32, v);
+            tmem_st32(lane_base + COL_ELO + b * BN + half * 32, lo);
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             tc_fence_before();
             mbar_arrive(&e_ready[b]);
         }
-        // ---- combine the two warpgroups' row sums; warpgroup 0 reads O out of TMEM once per CTA ----
-        if (wg == 1) rowsum_x[row] = rowsum;
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (wg == 0) {
-            rowsum += rowsum_x[row];
+        // ---- combine the four sub-groups' row sums; group 0 reads O out of TMEM once per CTA ----
+        const int sub = g * 2 + half;
+        if (sub > 0) rowsum_x[(sub - 1) * 128 + row] = rowsum;
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+        if (g == 0) {
             mbar_wait(o_full, 0);
             tc_fence_after();
             const int64_t grow = (int64_t)row0 + row;
-            if (n_tiles > 0) {
-#pragma unroll
-                for (int h = 0; h < D / 32; ++h) {
+            if (half < D / 32) {
+                if (n_tiles > 0) {
                     uint32_t v[32], c[32];
-                    tmem_ld32(lane_base + COL_O + h * 32, v);
-                    tmem_ld32(lane_base + COL_OC + h * 32, c);
+                    tmem_ld32(lane_base + COL_O + half * 32, v);
+                    tmem_ld32(lane_base + COL_OC + half * 32, c);
                     if (grow < n_r) {
-                        float4 *dst = reinterpret_cast<float4 *>(o_part + ((size_t)sp * n_r + grow) * D + h * 32);
+                        float4 *dst = reinterpret_cast<float4 *>(o_part + ((size_t)sp * n_r + grow) * D + half * 32);
 #pragma unroll
                         for (int k = 0; k < 8; ++k)
                             dst[k] = make_float4(__uint_as_float(v[4 * k]) + __uint_as_float(c[4 * k]),
@@ -400,11 +401,12 @@ softmax_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_r_hi, const __gri
                                                  __uint_as_float(v[4 * k + 2]) + __uint_as_float(c[4 * k + 2]),
                                                  __uint_as_float(v[4 * k + 3]) + __uint_as_float(c[4 * k + 3]));
                     }
+                } else if (grow < n_r) {
+                    for (int k = 0; k < 32; ++k) o_part[((size_t)sp * n_r + grow) * D + half * 32 + k] = 0.f;
                 }
-            } else if (grow < n_r) {
-                for (int k = 0; k < D; ++k) o_part[((size_t)sp * n_r + grow) * D + k] = 0.f;
             }
-            if (grow < n_r && rowsum_part != nullptr) rowsum_part[(size_t)sp * n_r + grow] = rowsum;
+            if (half == 0 && grow < n_r && rowsum_part != nullptr)
+                rowsum_part[(size_t)sp * n_r + grow] = rowsum + rowsum_x[row] + rowsum_x[128 + row] + rowsum_x[256 + row];
         }
     }
 
@@ -468,7 +470,7 @@ int launch_tc(const float *R_hi, const float *R_lo, int64_t n_r, const float *C_
     if ((rc = make_map(&mt_lo, CT_lo, D, n_c, ct_pitch, D)) != SSL_OK) return rc;
     constexpr int KCH = D / 32;
     const size_t smem = 1024 + 2 * (size_t)KCH * BM * 128 + (size_t)STAGES * 2 * KCH * BN * 128 + (size_t)STAGES * 2 * (BN / 32) * D * 128 +
-                        32 * sizeof(uint64_t) + 16 + 128 * sizeof(float);
+                        32 * sizeof(uint64_t) + 16 + 3 * 128 * sizeof(float);
     static bool configured = false;
     if (!configured) {
         SSL_CUDA(cudaFuncSetAttribute(softmax_gemm_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -49,10 +49,15 @@ struct PlanDev {
 
 __device__ __forceinline__ float sgnf(float x) { return (x > 0.f) ? 1.f : ((x < 0.f) ? -1.f : 0.f); }
 
-template <int G, int V, bool SHARED>
-__global__ void __launch_bounds__(kThreads) prop_kernel(PlanDev p, ssl_prop_args a) {
+// MODE 0: all views read the same input row and no view masks edges -> one accumulator, perturbed per view in the
+//         epilogue (SimGCL layer 1);  MODE 1: per-view inputs, no edge masks -> V accumulators, ONE weight per entry;
+// MODE 2: per-view edge masks -> V accumulators, V weights per entry.
+template <int G, int V, int MODE>
+__global__ void __launch_bounds__(kThreads, (V <= 3) ? 4 : 3) prop_kernel(PlanDev p, ssl_prop_args a) {
     constexpr int RPW = 32 / G;
+    constexpr bool SHARED = MODE == 0;
     constexpr int NA = SHARED ? 1 : V;
+    constexpr int NW = (MODE == 2) ? V : 1;        // distinct weights per entry
     const int lane = threadIdx.x & 31;
     const int gl = lane % G;
     const int grp = lane / G;
@@ -78,11 +83,11 @@ __global__ void __launch_bounds__(kThreads) prop_kernel(PlanDev p, ssl_prop_args
         const bool valid = pe < it.z;
         const int c = valid ? __ldg(p.colidx + pe) : 0;
         const float w = valid ? __ldg(p.vals + pe) : 0.f;
-        float wv[NA];
+        float wv[NW];
 #pragma unroll
-        for (int v = 0; v < NA; ++v) {
+        for (int v = 0; v < NW; ++v) {
             float f = w;
-            if (!SHARED) {
+            if (MODE == 2) {
                 const int mode = a.edge_mode[v];
                 if (mode == 1) {
                     const uint32_t kr = a.transpose ? (uint32_t)c : grow;
@@ -98,13 +103,13 @@ __global__ void __launch_bounds__(kThreads) prop_kernel(PlanDev p, ssl_prop_args
         const int cnt = min(G, it.z - base);
         for (int j = 0; j < cnt; j += 4) {
             int cj[4];
-            float wj[4][NA];
+            float wj[4][NW];
             float4 x[4][NA];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 cj[u] = __shfl_sync(gmask, c, j + u, G);
 #pragma unroll
-                for (int v = 0; v < NA; ++v) wj[u][v] = __shfl_sync(gmask, wv[v], j + u, G);
+                for (int v = 0; v < NW; ++v) wj[u][v] = __shfl_sync(gmask, wv[v], j + u, G);
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
@@ -112,13 +117,13 @@ __global__ void __launch_bounds__(kThreads) prop_kernel(PlanDev p, ssl_prop_args
 #pragma unroll
                 for (int v = 0; v < NA; ++v) {
                     x[u][v] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (lane_on && wj[u][v] != 0.f) x[u][v] = ssl::ldg4(xr + ((a.in_views == 1) ? 0 : v * dim));
+                    if (lane_on && wj[u][NW == 1 ? 0 : v] != 0.f) x[u][v] = ssl::ldg4(xr + ((a.in_views == 1) ? 0 : v * dim));
                 }
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u)
 #pragma unroll
-                for (int v = 0; v < NA; ++v) ssl::fma4(acc[v], wj[u][v], x[u][v]);
+                for (int v = 0; v < NA; ++v) ssl::fma4(acc[v], wj[u][NW == 1 ? 0 : v], x[u][v]);
         }
     }
     if (r < 0) return;
@@ -190,26 +195,27 @@ __global__ void __launch_bounds__(kThreads) prop_kernel(PlanDev p, ssl_prop_args
 }
 
 template <int G, int V>
-int launch_gv(const ssl_plan *plan, const ssl_prop_args &a, bool shared, cudaStream_t st) {
+int launch_gv(const ssl_plan *plan, const ssl_prop_args &a, int mode, cudaStream_t st) {
     PlanDev p{plan->colidx, plan->vals, plan->rev, plan->items, plan->long_info, plan->counters,
               plan->partial, plan->n_items, (uint32_t)plan->row_offset};
     constexpr int RPW = 32 / G;
     const int64_t items_per_block = (int64_t)(kThreads / 32) * RPW;
     const int64_t grid = (plan->n_items + items_per_block - 1) / items_per_block;
     if (grid == 0) return SSL_OK;
-    if (shared) prop_kernel<G, V, true><<<(unsigned)grid, kThreads, 0, st>>>(p, a);
-    else prop_kernel<G, V, false><<<(unsigned)grid, kThreads, 0, st>>>(p, a);
+    if (mode == 0) prop_kernel<G, V, 0><<<(unsigned)grid, kThreads, 0, st>>>(p, a);
+    else if (mode == 1) prop_kernel<G, V, 1><<<(unsigned)grid, kThreads, 0, st>>>(p, a);
+    else prop_kernel<G, V, 2><<<(unsigned)grid, kThreads, 0, st>>>(p, a);
     SSL_LAUNCH_CHECK("prop_kernel");
     return SSL_OK;
 }
 
 template <int G>
-int launch_g(const ssl_plan *plan, const ssl_prop_args &a, bool shared, cudaStream_t st) {
+int launch_g(const ssl_plan *plan, const ssl_prop_args &a, int mode, cudaStream_t st) {
     switch (a.n_views) {
-        case 1: return launch_gv<G, 1>(plan, a, shared, st);
-        case 2: return launch_gv<G, 2>(plan, a, shared, st);
-        case 3: return launch_gv<G, 3>(plan, a, shared, st);
-        case 4: return launch_gv<G, 4>(plan, a, shared, st);
+        case 1: return launch_gv<G, 1>(plan, a, mode, st);
+        case 2: return launch_gv<G, 2>(plan, a, mode, st);
+        case 3: return launch_gv<G, 3>(plan, a, mode, st);
+        case 4: return launch_gv<G, 4>(plan, a, mode, st);
     }
     return SSL_E_ARG;
 }
@@ -333,13 +339,13 @@ extern "C" int ssl_propagate_layer(const ssl_plan *plan, const ssl_prop_args *ar
     }
     for (int i = 0; i < a.n_sum_src; ++i)
         SSL_CHECK_ARG(a.sum_src[i] && (a.sum_src_views[i] == 1 || a.sum_src_views[i] == a.n_views), "ssl_propagate_layer: bad sum_src %d", i);
-    const bool shared = (a.in_views == 1) && !any_edge;
+    const int mode = any_edge ? 2 : ((a.in_views == 1) ? 0 : 1);
     cudaStream_t st = (cudaStream_t)stream;
     const int quads = a.dim / 4;
-    if (quads <= 4) return launch_g<4>(plan, a, shared, st);
-    if (quads <= 8) return launch_g<8>(plan, a, shared, st);
-    if (quads <= 16) return launch_g<16>(plan, a, shared, st);
-    return launch_g<32>(plan, a, shared, st);
+    if (quads <= 4) return launch_g<4>(plan, a, mode, st);
+    if (quads <= 8) return launch_g<8>(plan, a, mode, st);
+    if (quads <= 16) return launch_g<16>(plan, a, mode, st);
+    return launch_g<32>(plan, a, mode, st);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -570,18 +570,21 @@ def bpr_loss_sum(users: Rows, items: Rows, ancs, poss, negs) -> torch.Tensor:
     return _BprFn.apply(users, items, ancs, poss, negs, *_tokens(users, items))
 
 
-def choose_split(n_rtiles: int, n_ctiles: int, slots: int = 2 * 148) -> int:
-    """Number of chunks the streamed operand is cut into so that n_rtiles * n_split CTAs fill whole
-    waves of the resident-CTA slots (2 per SM at dim <= 64) with every CTA keeping >= 4 tiles."""
-    best, best_eff = 1, -1.0
+def choose_split(n_rtiles: int, n_ctiles: int, slots: int = 2 * 148, prefer_few: bool = False) -> int:
+    """Number of chunks the streamed operand is cut into so that n_rtiles * n_split CTAs fill whole waves of the
+    resident-CTA slots (2 per SM for the FFMA kernel at dim <= 64, 1 per SM for the tcgen05 kernel) with every
+    CTA keeping >= 4 tiles.  ``prefer_few``: among splits within 5 % of the best wave efficiency take the
+    smallest -- the tcgen05 kernel pays a resident-tile load + pipeline fill per CTA (measured 0.380 ms at 37
+    splits vs 0.339 ms at 9 for the bench's forward shape)."""
     max_split = max(1, min(n_ctiles // 4 if n_ctiles >= 4 else 1, 64))
+    effs = []
     for s in range(1, max_split + 1):
         ctas = n_rtiles * s
-        waves = math.ceil(ctas / slots)
-        eff = ctas / (waves * slots)
-        if eff > best_eff + 1e-9:
-            best, best_eff = s, eff
-    return best
+        effs.append((ctas / (math.ceil(ctas / slots) * slots), s))
+    best_eff = max(e for e, _ in effs)
+    if prefer_few:
+        return min(s for e, s in effs if e >= best_eff - 0.05)
+    return max(effs, key=lambda t: (round(t[0], 9), -t[1]))[1]
 
 
 def _nce_fwd(e1: Rows, e2: Rows, table: Rows, idx, idx2, tau, norm_mode, mean, deno_eps):
@@ -609,7 +612,7 @@ def _nce_fwd(e1: Rows, e2: Rows, table: Rows, idx, idx2, tau, norm_mode, mean, d
     else:
         t_t = torch.empty(npad // 64, d, 64, **f)
         a_hi = a_lo = t_hi = t_lo = a_thi = a_tlo = t_thi = t_tlo = None
-    n_split = choose_split((B + 127) // 128, npad // 64, slots=148 if use_tc else 296)
+    n_split = choose_split((B + 127) // 128, npad // 64, slots=148 if use_tc else 296, prefer_few=use_tc)
     rs_part, o_part = torch.zeros(n_split, B, **f), torch.zeros(n_split, B, d, **f)
     rowsum, obar, loss_b, out = torch.empty(B, **f), torch.empty(B, d, **f), torch.empty(B, **f), torch.empty((), **f)
     off = LOG2E / tau
@@ -666,7 +669,7 @@ def _nce_bwd(saved, g):
         if gt is not None and n > 0:
             colscale = torch.empty(ceil_to(B, 64), **f)
             check(lib.ssl_nce_colscale(rowsum.data_ptr(), B, g.data_ptr(), scale, colscale.data_ptr(), s), 'ssl_nce_colscale')
-            n_split = choose_split((n + 127) // 128, ceil_to(B, 64) // 64, slots=148 if tc else 296)
+            n_split = choose_split((n + 127) // 128, ceil_to(B, 64) // 64, slots=148 if tc else 296, prefer_few=bool(tc))
             dt_part = torch.empty(n_split, n, d, **f)
             with _timed('nce_gemm_bwd', dict(B=B, n=n, dim=d, tc=bool(tc))):
                 if tc:
