@@ -36,21 +36,30 @@ class Trainer(object):
             raise NotImplementedError("only 'adam' is supported (trainer.py:47)")
 
     def train_epoch(self, model, epoch_idx):
+        """Same loop and same logged numbers as trainer.py:51-84.  The reference reads ``loss.item()`` and
+        ``float(v)`` for every loss term right after ``cal_loss`` (:66, :72), i.e. 1 + n_terms blocking device
+        syncs per step; here the step's scalars are copied device->pinned host asynchronously and summed when
+        the copy has landed (one step later), so the host keeps enqueueing while the GPU works."""
         train_dataloader = self.data_handler.train_dataloader
         train_dataloader.dataset.sample_negs()
         loss_log_dict = {}
         ep_loss = 0
         model.train()
+        reader = LossReader(configs['device'])
         for _, tem in enumerate(train_dataloader):
             self.optimizer.zero_grad()
-            batch_data = list(map(lambda x: x.long().to(configs['device']), tem))
+            batch_data = list(map(lambda x: x.long().to(configs['device'], non_blocking=True), tem))
             loss, loss_dict = model.cal_loss(batch_data)
-            ep_loss += loss.item()
             loss.backward()
             self.optimizer.step()
-            for loss_name in loss_dict:
-                _loss_val = float(loss_dict[loss_name]) / len(train_dataloader)
-                loss_log_dict[loss_name] = loss_log_dict.get(loss_name, 0.0) + _loss_val
+            for done in reader.push(loss, loss_dict):
+                ep_loss += done[0]
+                for loss_name, val in done[1].items():
+                    loss_log_dict[loss_name] = loss_log_dict.get(loss_name, 0.0) + val / len(train_dataloader)
+        for done in reader.flush():
+            ep_loss += done[0]
+            for loss_name, val in done[1].items():
+                loss_log_dict[loss_name] = loss_log_dict.get(loss_name, 0.0) + val / len(train_dataloader)
         if self.logger is not None:
             self.logger.log_loss(epoch_idx, loss_log_dict, save_to_log=configs['train'].get('log_loss', True))
         return ep_loss, loss_log_dict
@@ -93,6 +102,39 @@ class Trainer(object):
         if self.logger is not None:
             self.logger.log_eval(result, ks, data_type='Validation set', epoch_idx=epoch_idx)
         return result
+
+
+class LossReader:
+    """Device -> pinned-host reads of a step's loss scalars without blocking the enqueueing thread: ``push``
+    starts the copy of this step's values and returns the steps whose copies have already landed."""
+
+    def __init__(self, device, depth: int = 2):
+        self.device, self.depth, self.queue = device, depth, []
+
+    def push(self, loss, loss_dict):
+        names = list(loss_dict)
+        vals = torch.stack([loss.detach()] + [torch.as_tensor(loss_dict[n]).detach().to(loss.device).reshape(()) for n in names])
+        host = torch.empty(vals.shape, dtype=vals.dtype, pin_memory=True)
+        host.copy_(vals, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self.queue.append((ev, host, names))
+        out = []
+        while len(self.queue) > self.depth or (self.queue and self.queue[0][0].query()):
+            out.append(self._pop())
+        return out
+
+    def _pop(self):
+        ev, host, names = self.queue.pop(0)
+        ev.synchronize()
+        v = host.tolist()
+        return v[0], dict(zip(names, v[1:]))
+
+    def flush(self):
+        out = []
+        while self.queue:
+            out.append(self._pop())
+        return out
 
 
 def topk(preds: torch.Tensor, k: int, return_values: bool = False):
