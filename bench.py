@@ -118,6 +118,14 @@ class ClockSampler:
                 'samples': len(self.sm), 'power_w_max': max(self.power) if self.power else None}
 
 
+def ncu_traffic(kernel, key):
+    """DRAM bytes per launch from the committed ncu capture of this workload (profiles/traffic.json), else None."""
+    p = os.path.join(ROOT, 'profiles', 'traffic.json')
+    if os.path.exists(p):
+        return json.load(open(p)).get(kernel, {}).get(key)
+    return None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(p):
@@ -351,7 +359,7 @@ def run_ours(args):
     achieved = prop_bytes / (prop_ms * 1e-3) / 1e9 if prop else None
     roofline = {'kernel': 'prop_kernel (ssl_propagate_layer; all forward + transposed-backward launches of the timed steps)',
                 'bound': 'hbm', 'achieved': achieved, 'peak': peaks['hbm_gbs'], 'peak_kind': peak_kind + ' (burst copy)', 'unit': 'GB/s',
-                'frac': (achieved / peaks['hbm_gbs']) if achieved else None, 'traffic': None,
+                'frac': (achieved / peaks['hbm_gbs']) if achieved else None, 'traffic': ncu_traffic('prop_kernel', f'views{views}_dim{d}_{graph}'),
                 'avg_launch_ms': prop_ms / len(prop) if prop else None, 'alg_bytes_per_launch': prop_bytes / len(prop) if prop else None,
                 'launches_per_step': len(prop) / K, 'share_of_step': prop_ms / K / prof_ms if prof_ms else None,
                 'note': 'the 41 MB/view tables of this graph fit the 126 MB L2, so achieved counts L2 hits and can exceed the HBM peak; '

@@ -1,0 +1,86 @@
+"""Parity at BASELINE.json's full sizes (synthetic graphs with the bundled datasets' shapes): the CUDA path against the
+oracle run live on the host cores with the same weights, batch and injected noise / masks."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import torch
+
+from oracle import cf_oracle as O
+import ssl_test_helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(model_name, graph, hp, seed=7):
+    from sslrec_b200.datagen import named_graph
+    rows, cols, U, I = named_graph(graph, seed=2023)
+    case = dict(rows=rows, cols=cols, n_user=U, n_item=I, dim=hp['embedding_size'], batch=4096)
+    g = torch.Generator().manual_seed(seed)
+    d = hp['embedding_size']
+    case['user_e'] = (torch.rand(U, d, generator=g) * 2 - 1) * float(np.sqrt(6.0 / (U + d)))
+    case['item_e'] = (torch.rand(I, d, generator=g) * 2 - 1) * float(np.sqrt(6.0 / (I + d)))
+    rs = np.random.RandomState(seed)
+    pick = rs.randint(0, len(rows), size=4096)
+    case['ancs'], case['poss'], case['negs'] = rows[pick], cols[pick], rs.randint(0, I, size=4096).astype(np.int64)
+    adj = O.normalized_adjacency(rows, cols, U, I)
+    return case, adj, g
+
+
+def test_simgcl_amazon_shape_step_matches_oracle():
+    hp = dict(layer_num=3, embedding_size=64, temperature=0.2, eps=0.9, cl_weight=1.0e-2, reg_weight=1.0e-6, keep_rate=1.0)
+    case, adj, g = _setup('simgcl', 'amazon', hp)
+    uniforms = [[torch.rand(adj.n, 64, generator=g) for _ in range(3)] for _ in range(2)]
+    inj = {'noise_u': [[u.cuda() for u in view] for view in uniforms]}
+    model, _ = H.make_model('simgcl', case, hp, inject=inj)
+    model.load_state_dict({'user_embeds': case['user_e'], 'item_embeds': case['item_e']})
+    batch = [torch.from_numpy(case[k]).cuda() for k in ('ancs', 'poss', 'negs')]
+    loss, parts = model.cal_loss(batch)
+    loss.backward()
+    ue, ie = case['user_e'].clone().requires_grad_(True), case['item_e'].clone().requires_grad_(True)
+    torch.set_num_threads(min(32, torch.get_num_threads()))
+    ref, rparts = O.simgcl_loss(adj, ue, ie, tuple(torch.from_numpy(case[k]) for k in ('ancs', 'poss', 'negs')), 3, hp['reg_weight'],
+                                hp['cl_weight'], hp['temperature'], hp['eps'], uniforms[0], uniforms[1])
+    ref.backward()
+    assert abs(loss.item() - ref.item()) <= 1e-5, (loss.item(), ref.item())
+    for k in rparts:
+        assert abs(float(parts[k]) - float(rparts[k])) <= 1e-5, k
+    for got, want in ((model.user_embeds.grad, ue.grad), (model.item_embeds.grad, ie.grad)):
+        H.close(got, want, 5e-4, 1e-5 * want.abs().max().item(), 'full-size gradient')
+    # evaluation on the same weights: top-40 of 1024 users against torch.topk of the oracle's scores
+    from sslrec_b200.trainer import topk
+    model.eval()
+    users = torch.arange(1024)
+    with torch.no_grad():
+        preds = model.full_predict([users.cuda(), None])
+        e = O.lightgcn_embeds(adj.torch_coo(), torch.cat([case['user_e'], case['item_e']], 0), 3)
+        want = e[:1024] @ e[adj.n_user:].T
+    idx, val = topk(preds, 40, return_values=True)
+    wv, wi = torch.topk(want, 40)
+    H.close(val, wv, 1e-5, 1e-7, 'top-40 scores')
+    gap = (wv[:, :-1] - wv[:, 1:]).abs()
+    near = gap <= 2e-6 * wv[:, :-1].abs().clamp(min=1e-3)
+    ok = torch.ones_like(wi, dtype=torch.bool)
+    ok[:, :-1] &= ~near
+    ok[:, 1:] &= ~near
+    ok[:, -1] = False
+    assert (idx.cpu()[ok] == wi[ok]).all() and ok.float().mean() > 0.9
+
+
+def test_sgl_yelp_shape_rng_augmentation_statistics():
+    """In-kernel RNG edge drop at keep 0.5 on the yelp-shaped graph: the kept fraction and the step's determinism."""
+    hp = dict(layer_num=3, embedding_size=64, temperature=0.2, cl_weight=1.0, reg_weight=1.0e-5, keep_rate=0.5, augmentation='edge_drop')
+    case, adj, g = _setup('sgl', 'yelp', hp)
+    model, _ = H.make_model('sgl', case, hp)
+    model.load_state_dict({'user_embeds': case['user_e'], 'item_embeds': case['item_e']})
+    batch = [torch.from_numpy(case[k]).cuda() for k in ('ancs', 'poss', 'negs')]
+    from sslrec_b200 import engine as E
+    losses = []
+    for _ in range(2):
+        model._seeds = E.SeedStream(2023)
+        loss, _ = model.cal_loss(batch)
+        losses.append(loss.item())
+    assert losses[0] == losses[1]                       # same seeds -> bit-identical loss (fixed summation order, counter-based RNG)
+    ones = torch.ones(adj.n, 64, device='cuda')
+    view = model.edge_dropper.view(0.5, 99)
+    kept = E.spmm(model._plan(), ones, view)[:, 0].double().sum().item() / float(adj.vals.astype(np.float64).sum())
+    assert abs(kept - 0.5) < 0.01
