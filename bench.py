@@ -38,6 +38,10 @@ WORKLOADS = {
     'lightgcn-gowalla': ('lightgcn', 'gowalla', dict(layer_num=3, embedding_size=64, reg_weight=1.0e-8, keep_rate=0.5)),
     'sgl-yelp': ('sgl', 'yelp', dict(layer_num=3, embedding_size=64, temperature=0.2, cl_weight=1.0, reg_weight=1.0e-5,
                                      keep_rate=0.5, augmentation='edge_drop')),
+    'ncl-amazon': ('ncl', 'amazon', dict(layer_num=3, embedding_size=64, high_order=2, reg_weight=1.0e-7, proto_weight=1.0e-4,
+                                         struct_weight=1.0e-3, temperature=0.1, epoch_period=3, cluster_num=50, keep_rate=1.0)),
+    'hccf-amazon': ('hccf', 'amazon', dict(layer_num=2, embedding_size=64, reg_weight=1.0e-7, cl_weight=1.0, temperature=0.1,
+                                           keep_rate=0.5, mult=1.0, hyper_num=128, leaky=0.5)),
 }
 BATCH = 4096
 
@@ -219,6 +223,8 @@ def run_ours(args):
     rows, cols, n_user, n_item = graph_arrays(graph)
     cfg = default_config(model_name, **hp)
     cfg['train']['batch_size'] = BATCH
+    if model_name == 'ncl':
+        cfg['train']['loss'] = 'pairwise_with_epoch_flag'
     load_config(base=cfg, device=str(dev))
     trn = sp.coo_matrix((np.ones(len(rows), dtype=np.float32), (rows, cols)), shape=(n_user, n_item))
     dh = DataHandlerGeneralCF(trn)
@@ -237,10 +243,18 @@ def run_ours(args):
     host_batches = [torch.from_numpy(b).pin_memory() for b in make_batches(rows, cols, n_item, K + W)]
     dev_batches = [b.to(dev) for b in host_batches]
 
+    flag = torch.zeros(BATCH, dtype=torch.int64, device=dev)
+
+    def as_batch(b):
+        return [b[0], b[1], b[2], flag] if model_name == 'ncl' else [b[0], b[1], b[2]]
+    if model_name == 'ncl':
+        model.kmeans.iters = 20                      # the clustering runs once, before the timed region (ncl.py:73-74)
+        model._cluster()
+
     def step_resident(i):
         opt.zero_grad()
         b = dev_batches[i]
-        loss, parts = model.cal_loss([b[0], b[1], b[2]])
+        loss, parts = model.cal_loss(as_batch(b))
         loss.backward()
         opt.step()
         return loss
@@ -255,7 +269,7 @@ def run_ours(args):
         step's loss scalars copied device -> pinned host asynchronously (read one step later)."""
         opt.zero_grad()
         b = host_batches[i].to(dev, non_blocking=True)
-        loss, parts = model.cal_loss([b[0], b[1], b[2]])
+        loss, parts = model.cal_loss(as_batch(b))
         loss.backward()
         opt.step()
         if e2e_sampler[0] is not None:
@@ -265,7 +279,7 @@ def run_ours(args):
     def step_e2e(i):
         opt.zero_grad()
         b = host_batches[i].to(dev, non_blocking=True)           # trainer.py:64
-        loss, parts = model.cal_loss([b[0], b[1], b[2]])
+        loss, parts = model.cal_loss(as_batch(b))
         v = loss.item()                                          # trainer.py:66 (D2H sync)
         loss.backward()
         opt.step()
@@ -386,7 +400,8 @@ def run_ours(args):
             roofline_nce = {'kernel': 'softmax_gemm_kernel (ssl_softmax_gemm, forward + backward launches)', 'bound': 'fp32_fma', 'achieved': eq_tf,
                             'peak': fp32_peak, 'peak_kind': f'148 SM x 128 FMA/clk x 2 x {sm_mhz:.0f} MHz', 'unit': 'TFLOP/s',
                             'frac': eq_tf / fp32_peak, 'flop_per_step': nce_flops_step, 'share_of_step': nce_ms / K / prof_ms}
-    emb_per_step = 2.0 * views * L * nnz if model_name != 'sgl' else 2.0 * L * nnz * (1 + 2 * hp['keep_rate'])
+    n_prop_layers = max(L, 2 * hp.get('high_order', 0))
+    emb_per_step = 2.0 * views * n_prop_layers * nnz if model_name != 'sgl' else 2.0 * L * nnz * (1 + 2 * hp['keep_rate'])
 
     # ---- CPU baseline on this box's host cores (bounded sample) ----
     cpu = None
