@@ -322,6 +322,10 @@ def run_ours(args):
             ms = float(t.item())
         return ms / K, launches, clocks
 
+    # burn-in: allocator cache, module loading, NCCL channels and GPU clocks settle before anything is timed
+    for i in range(30):
+        step_resident(i % (K + W))
+    barrier()
     ms_res, launches, clocks = timed(step_resident)
     # e2e is timed WITHOUT clock sampling (one NVML sample costs ~14 ms of host time, which the per-step
     # syncs of this loop would expose); its clocks come from a short sampled replay of the same loop
