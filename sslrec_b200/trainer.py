@@ -110,24 +110,33 @@ class LossReader:
 
     def __init__(self, device, depth: int = 2):
         self.device, self.depth, self.queue = device, depth, []
+        self._free = []            # pinned staging buffers are recycled: cudaHostAlloc per step costs milliseconds
+
+    def _staging(self, n):
+        for k, h in enumerate(self._free):
+            if h.numel() >= n:
+                return self._free.pop(k)[:n] if h.numel() == n else self._free.pop(k)
+        return torch.empty(max(n, 8), dtype=torch.float32, pin_memory=True)
 
     def push(self, loss, loss_dict):
         names = list(loss_dict)
         vals = torch.stack([loss.detach()] + [torch.as_tensor(loss_dict[n]).detach().to(loss.device).reshape(()) for n in names])
-        host = torch.empty(vals.shape, dtype=vals.dtype, pin_memory=True)
+        buf = self._staging(vals.numel())
+        host = buf[:vals.numel()]
         host.copy_(vals, non_blocking=True)
         ev = torch.cuda.Event()
         ev.record()
-        self.queue.append((ev, host, names))
+        self.queue.append((ev, host, names, buf))
         out = []
         while len(self.queue) > self.depth or (self.queue and self.queue[0][0].query()):
             out.append(self._pop())
         return out
 
     def _pop(self):
-        ev, host, names = self.queue.pop(0)
+        ev, host, names, buf = self.queue.pop(0)
         ev.synchronize()
         v = host.tolist()
+        self._free.append(buf)
         return v[0], dict(zip(names, v[1:]))
 
     def flush(self):
