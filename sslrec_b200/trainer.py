@@ -115,7 +115,7 @@ class LossReader:
     def _staging(self, n):
         for k, h in enumerate(self._free):
             if h.numel() >= n:
-                return self._free.pop(k)[:n] if h.numel() == n else self._free.pop(k)
+                return self._free.pop(k)
         return torch.empty(max(n, 8), dtype=torch.float32, pin_memory=True)
 
     def push(self, loss, loss_dict):
