@@ -60,6 +60,7 @@ class BaseModel(nn.Module):
     # ---- runtime shared by the drop-in models ----------------------------------------------------
     def _init_runtime(self, data_handler):
         from . import engine as E
+        self._trn_mat = getattr(data_handler, 'trn_mat', None)
         self._seeds = E.SeedStream(configs.get('train', {}).get('seed', 2023))
         self._plans = {}
         self._state = None
@@ -80,17 +81,36 @@ class BaseModel(nn.Module):
                 self._plans[key] = GraphPlan.from_torch_adj(adj, dev, need_rev=self._inject is not None)
         return self._plans[key]
 
+    def _train_csr(self, device):
+        """Training interactions as a device CSR (int32), built once: the mask of ``_mask_predict`` without the
+        dense [Bt, I] float64 rows the reference ships per eval batch (datasets_general_cf.py:64-68)."""
+        if getattr(self, '_trn_csr_dev', None) is None or self._trn_csr_dev[0].device != device:
+            import numpy as np
+            import scipy.sparse as sp
+            m = sp.csr_matrix(self._trn_mat)
+            m.sort_indices()
+            self._trn_csr_dev = (torch.from_numpy(m.indptr.astype(np.int32)).to(device), torch.from_numpy(m.indices.astype(np.int32)).to(device))
+        return self._trn_csr_dev
+
     def _predict(self, user_embeds, item_embeds, batch_data):
-        """E_u[users] E_i^T with the training positives masked to -1e8 (lightgcn.py:61-65,
-        base_model.py:35-36) in one kernel; no [Bt, I] temporaries besides the result."""
+        """E_u[users] E_i^T with the training positives masked to -1e8 (lightgcn.py:61-65, base_model.py:35-36) in
+        one kernel; no [Bt, I] temporaries besides the result.  ``train_mask``: the reference's dense [Bt, I] 0/1
+        tensor, or None = no masking, or the string 'train' = mask the user's training items from the device CSR."""
         pck_users, train_mask = batch_data
         pck_users = pck_users.long().contiguous()
         n_b = pck_users.shape[0]
         preds = torch.empty(n_b, self.item_num, device=user_embeds.device, dtype=torch.float32)
-        mask = None if train_mask is None else train_mask.long().contiguous()
+        mask, rowptr, cols = None, None, None
+        if isinstance(train_mask, str):
+            if train_mask != 'train' or getattr(self, '_trn_mat', None) is None:
+                raise ValueError("train_mask must be a tensor, None or 'train' (needs data_handler.trn_mat)")
+            rowptr, cols = self._train_csr(preds.device)
+        elif train_mask is not None:
+            mask = train_mask.long().contiguous()
         with torch.cuda.device(preds.device):
             check(lib.ssl_predict_mask(user_embeds.data_ptr(), user_embeds.stride(0), item_embeds.data_ptr(), item_embeds.stride(0),
                                        pck_users.data_ptr(), n_b, self.item_num, self.embedding_size,
-                                       None if mask is None else mask.data_ptr(), None, None, preds.data_ptr(),
+                                       None if mask is None else mask.data_ptr(), None if rowptr is None else rowptr.data_ptr(),
+                                       None if cols is None else cols.data_ptr(), preds.data_ptr(),
                                        torch.cuda.current_stream(preds.device).cuda_stream), 'ssl_predict_mask')
         return preds

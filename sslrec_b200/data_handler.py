@@ -86,7 +86,10 @@ class PairwiseWEpochFlagTrnData(PairwiseTrnData):
 class AllRankTstData(data.Dataset):
     """Test users with their held-out positives and a dense train-mask row (datasets_general_cf.py:46-68)."""
 
-    def __init__(self, coomat, trn_mat):
+    def __init__(self, coomat, trn_mat, dense_mask: bool = True):
+        """dense_mask = False: yield only the user id; the model masks from its device CSR of the training matrix
+        (``full_predict([users, 'train'])``) instead of a dense float64 [I] row per user built on the host."""
+        self.dense_mask = dense_mask
         self.csrmat = (sp.csr_matrix(trn_mat) != 0) * 1.0
         coomat = sp.coo_matrix(coomat)
         order = np.argsort(coomat.row, kind='stable')
@@ -102,6 +105,8 @@ class AllRankTstData(data.Dataset):
 
     def __getitem__(self, idx):
         pck_user = self.test_users[idx]
+        if not self.dense_mask:
+            return pck_user
         pck_mask = np.reshape(self.csrmat[pck_user].toarray(), [-1])
         return pck_user, pck_mask
 
@@ -129,7 +134,8 @@ class DataHandlerGeneralCF:
         else:
             raise NotImplementedError(configs['train']['loss'])
         self.train_dataloader = data.DataLoader(trn_data, batch_size=configs['train']['batch_size'], shuffle=True, num_workers=0)
+        dense = configs['test'].get('dense_mask', True)      # optional key: False = mask on device from the training CSR
         if val_mat is not None:
-            self.valid_dataloader = data.DataLoader(AllRankTstData(val_mat, trn_mat), batch_size=configs['test']['batch_size'], shuffle=False, num_workers=0)
+            self.valid_dataloader = data.DataLoader(AllRankTstData(val_mat, trn_mat, dense), batch_size=configs['test']['batch_size'], shuffle=False, num_workers=0)
         if tst_mat is not None:
-            self.test_dataloader = data.DataLoader(AllRankTstData(tst_mat, trn_mat), batch_size=configs['test']['batch_size'], shuffle=False, num_workers=0)
+            self.test_dataloader = data.DataLoader(AllRankTstData(tst_mat, trn_mat, dense), batch_size=configs['test']['batch_size'], shuffle=False, num_workers=0)

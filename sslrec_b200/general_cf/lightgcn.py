@@ -15,8 +15,6 @@ class LightGCN(BaseModel):
     def __init__(self, data_handler):
         super().__init__(data_handler)
         self.adj = data_handler.torch_adj
-        self._trn_mat = getattr(data_handler, 'trn_mat', None)
-
         self.layer_num = configs['model']['layer_num']
         self.reg_weight = configs['model']['reg_weight']
         self.keep_rate = configs['model']['keep_rate']

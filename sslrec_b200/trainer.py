@@ -84,8 +84,12 @@ class Trainer(object):
         ds = loader.dataset
         n_users = len(ds.test_users)
         for tem in loader:
+            if not isinstance(tem, (list, tuple)):
+                tem = [tem]
             users = tem[0].numpy().tolist()
             batch_data = list(map(lambda x: x.long().to(configs['device']), tem))
+            if len(batch_data) == 1:
+                batch_data.append('train')                   # dataset built with dense_mask=False: mask from the device CSR
             preds = model.full_predict(batch_data)
             top = topk(preds, max(ks)).cpu().numpy()
             for bi, u in enumerate(users):

@@ -135,3 +135,14 @@ def test_trainer_epochs_and_evaluate(name):
     res = tr.evaluate(model)
     assert set(res) == {'recall', 'ndcg'} and all(0.0 <= v <= 1.0 for m in res.values() for v in m)
     assert res['recall'][2] >= res['recall'][0]          # recall@40 >= recall@10
+    # the device-CSR mask (no dense host rows) gives exactly the same scores and metrics as the reference's dense mask
+    from sslrec_b200.data_handler import AllRankTstData
+    import torch.utils.data as tdata
+    lean = tdata.DataLoader(AllRankTstData(val, trn, dense_mask=False), batch_size=256, shuffle=False)
+    res2 = tr.evaluate(model, loader=lean)
+    for m in res:
+        assert np.array_equal(res[m], res2[m])
+    users = torch.arange(64).cuda()
+    dense = torch.from_numpy((trn.tocsr()[:64].toarray() != 0).astype(np.int64)).cuda()
+    with torch.no_grad():
+        assert torch.equal(model.full_predict([users, dense]), model.full_predict([users, 'train']))
