@@ -61,12 +61,15 @@ SSL_API int64_t ssl_launch_count(void);
  *   d_rev     device int32 [nnz] or NULL: position of the reverse entry (col,row); only needed
  *             when an *injected* edge mask is used together with transpose = 1
  *   row_offset  global id of local row 0 (row-sharded multi-GPU; 0 on one GPU)
+ *   side_split  global row id where the second side of the bipartite graph starts (|U|), or 0: the work list
+ *               then runs all rows of one side before the other, so concurrently running CTAs gather from one
+ *               half of the table only (user rows read item rows and vice versa) -- halves the L2 working set
  * ------------------------------------------------------------------------------------------ */
 typedef struct ssl_plan ssl_plan;
 
 SSL_API int ssl_plan_create(ssl_plan **out, const int32_t *h_rowptr, const int32_t *d_colidx, const float *d_vals,
                     const int32_t *d_rev, int64_t n_rows, int64_t n_cols, int64_t nnz, int64_t row_offset,
-                    void *stream);
+                    int64_t side_split, void *stream);
 SSL_API int ssl_plan_destroy(ssl_plan *plan);
 /* work-list statistics: out[0]=items, out[1]=split rows, out[2]=segments, out[3]=max row nnz */
 SSL_API int ssl_plan_stats(const ssl_plan *plan, int64_t out[4]);

@@ -53,7 +53,7 @@ def _load():
         'ssl_version': (C.c_int, []),
         'ssl_last_error': (C.c_char_p, []),
         'ssl_launch_count': (i64, []),
-        'ssl_plan_create': (C.c_int, [C.POINTER(vp), vp, vp, vp, vp, i64, i64, i64, i64, vp]),
+        'ssl_plan_create': (C.c_int, [C.POINTER(vp), vp, vp, vp, vp, i64, i64, i64, i64, i64, vp]),
         'ssl_plan_destroy': (C.c_int, [vp]),
         'ssl_plan_stats': (C.c_int, [vp, c_i64p]),
         'ssl_propagate_layer': (C.c_int, [vp, C.POINTER(PropArgs), vp]),

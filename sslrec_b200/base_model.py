@@ -76,9 +76,9 @@ class BaseModel(nn.Module):
             if dev.type != 'cuda':
                 raise RuntimeError('sslrec_b200 models run on CUDA only (move the model with .to("cuda")); there is no CPU path')
             if self.comm is not None and self.comm.shard_propagation:
-                self._plans[key] = self.comm.make_plan(adj, dev)
+                self._plans[key] = self.comm.make_plan(adj, dev, side_split=self.user_num)
             else:
-                self._plans[key] = GraphPlan.from_torch_adj(adj, dev, need_rev=self._inject is not None)
+                self._plans[key] = GraphPlan.from_torch_adj(adj, dev, need_rev=self._inject is not None, side_split=self.user_num)
         return self._plans[key]
 
     def _train_csr(self, device):

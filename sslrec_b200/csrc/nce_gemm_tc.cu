@@ -35,7 +35,8 @@
 
 namespace {
 
-constexpr int BM = 128, BN = 64, STAGES = 2;
+constexpr int BM = 128, BN = 64;
+constexpr int ST1 = 3, ST2 = 2;        // stages of ring 1 (GEMM1's B, gates the S pipeline) and ring 2 (GEMM2's B); 64 + 96 + 64 KB at d = 64
 constexpr int kNumThreads = 640;       // warps 0-3: TMA, MMA1, TMA, MMA2; warps 4-11 and 12-19: two epilogue groups of 256 threads
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t COL_S = 0, COL_EHI = 128, COL_ELO = 256, COL_O = 384, COL_OC = 448;
@@ -218,10 +219,10 @@ softmax_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_r_hi, const __gri
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t *r_hi = smem, *r_lo = smem + R_BYTES;
     uint8_t *ring1 = smem + 2 * R_BYTES;                // stage s: C tile row-major, hi then lo (GEMM1's B, K-major)
-    uint8_t *ring2 = ring1 + STAGES * 2 * C_BYTES;      // stage s: C^T tile, hi then lo          (GEMM2's B, K-major)
-    uint64_t *bars = reinterpret_cast<uint64_t *>(ring2 + STAGES * 2 * T_BYTES);
-    uint64_t *full1 = bars, *empty1 = full1 + STAGES, *full2 = empty1 + STAGES, *empty2 = full2 + STAGES;
-    uint64_t *s_full = empty2 + STAGES, *s_free = s_full + 2, *e_ready = s_free + 2, *e_free = e_ready + 2, *r_full = e_free + 2, *o_full = r_full + 1;
+    uint8_t *ring2 = ring1 + ST1 * 2 * C_BYTES;      // stage s: C^T tile, hi then lo          (GEMM2's B, K-major)
+    uint64_t *bars = reinterpret_cast<uint64_t *>(ring2 + ST2 * 2 * T_BYTES);
+    uint64_t *full1 = bars, *empty1 = full1 + ST1, *full2 = empty1 + ST1, *empty2 = full2 + ST2;
+    uint64_t *s_full = empty2 + ST2, *s_free = s_full + 2, *e_ready = s_free + 2, *e_free = e_ready + 2, *r_full = e_free + 2, *o_full = r_full + 1;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(o_full + 1);
     float *rowsum_x = reinterpret_cast<float *>(tmem_slot + 4);     // [3][128] partial row sums of the other epilogue sub-groups
 
@@ -239,9 +240,11 @@ softmax_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_r_hi, const __gri
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_c_lo));
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_ct_hi));
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_ct_lo));
-        for (int s = 0; s < STAGES; ++s) {
+        for (int s = 0; s < ST1; ++s) {
             mbar_init(&full1[s], 1);
             mbar_init(&empty1[s], 1);
+        }
+        for (int s = 0; s < ST2; ++s) {
             mbar_init(&full2[s], 1);
             mbar_init(&empty2[s], 1);
         }
@@ -272,8 +275,8 @@ softmax_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_r_hi, const __gri
             tma_load_2d(r_lo + c * R_CHUNK, &map_r_lo, c * 32, row0, r_full);
         }
         for (int i = 0; i < n_tiles; ++i) {
-            const int s = i % STAGES;
-            mbar_wait(&empty1[s], ((i / STAGES) & 1) ^ 1);
+            const int s = i % ST1;
+            mbar_wait(&empty1[s], ((i / ST1) & 1) ^ 1);
             uint8_t *hi = ring1 + s * 2 * C_BYTES, *lo = hi + C_BYTES;
             mbar_expect_tx(&full1[s], 2 * C_BYTES);
             for (int c = 0; c < KCH; ++c) {
@@ -284,8 +287,8 @@ softmax_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_r_hi, const __gri
     } else if (warp == 2 && lane == 0) {
         // ===================== TMA producer, ring 2: the transposed C tiles [d, 64] =====================
         for (int i = 0; i < n_tiles; ++i) {
-            const int s = i % STAGES;
-            mbar_wait(&empty2[s], ((i / STAGES) & 1) ^ 1);
+            const int s = i % ST2;
+            mbar_wait(&empty2[s], ((i / ST2) & 1) ^ 1);
             uint8_t *hi = ring2 + s * 2 * T_BYTES, *lo = hi + T_BYTES;
             mbar_expect_tx(&full2[s], 2 * T_BYTES);
             for (int c = 0; c < JCH; ++c) {
@@ -299,8 +302,8 @@ softmax_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_r_hi, const __gri
         const uint32_t r_hi_a = smem_u32(r_hi), r_lo_a = smem_u32(r_lo);
         mbar_wait(r_full, 0);
         for (int i = 0; i < n_tiles; ++i) {
-            const int s = i % STAGES, b = i & 1;
-            mbar_wait(&full1[s], (i / STAGES) & 1);
+            const int s = i % ST1, b = i & 1;
+            mbar_wait(&full1[s], (i / ST1) & 1);
             mbar_wait(&s_free[b], ((i >> 1) & 1) ^ 1);           // the epilogue of tile i-2 has read S out of this buffer
             tc_fence_after();
             const uint32_t c_hi_a = smem_u32(ring1 + s * 2 * C_BYTES), c_lo_a = c_hi_a + C_BYTES;
@@ -324,9 +327,9 @@ softmax_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_r_hi, const __gri
         // ===================== MMA issuer 2: O += E C  (A = E from TMEM, B = C^T tile) =====================
         constexpr uint32_t idesc2 = instr_desc(BM, D, 0);       // O[128 x d] += E (TMEM, K = 64) x C^T (K-major)
         for (int j = 0; j < n_tiles; ++j) {
-            const int s = j % STAGES, b = j & 1;
+            const int s = j % ST2, b = j & 1;
             mbar_wait(&e_ready[b], (j >> 1) & 1);
-            mbar_wait(&full2[s], (j / STAGES) & 1);
+            mbar_wait(&full2[s], (j / ST2) & 1);
             tc_fence_after();
             const uint32_t t_hi_a = smem_u32(ring2 + s * 2 * T_BYTES), t_lo_a = t_hi_a + T_BYTES;
             const uint32_t e_hi = tmem + COL_EHI + b * BN, e_lo = tmem + COL_ELO + b * BN;
@@ -469,7 +472,7 @@ int launch_tc(const float *R_hi, const float *R_lo, int64_t n_r, const float *C_
     if ((rc = make_map(&mt_hi, CT_hi, D, n_c, ct_pitch, D)) != SSL_OK) return rc;
     if ((rc = make_map(&mt_lo, CT_lo, D, n_c, ct_pitch, D)) != SSL_OK) return rc;
     constexpr int KCH = D / 32;
-    const size_t smem = 1024 + 2 * (size_t)KCH * BM * 128 + (size_t)STAGES * 2 * KCH * BN * 128 + (size_t)STAGES * 2 * (BN / 32) * D * 128 +
+    const size_t smem = 1024 + 2 * (size_t)KCH * BM * 128 + (size_t)ST1 * 2 * KCH * BN * 128 + (size_t)ST2 * 2 * (BN / 32) * D * 128 +
                         32 * sizeof(uint64_t) + 16 + 3 * 128 * sizeof(float);
     static bool configured = false;
     if (!configured) {

@@ -224,7 +224,7 @@ int launch_g(const ssl_plan *plan, const ssl_prop_args &a, int mode, cudaStream_
 
 extern "C" int ssl_plan_create(ssl_plan **out, const int32_t *h_rowptr, const int32_t *d_colidx, const float *d_vals,
                                const int32_t *d_rev, int64_t n_rows, int64_t n_cols, int64_t nnz, int64_t row_offset,
-                               void *stream) {
+                               int64_t side_split, void *stream) {
     SSL_CHECK_ARG(out && h_rowptr, "ssl_plan_create: null argument");
     SSL_CHECK_ARG(nnz == 0 || (d_colidx && d_vals), "ssl_plan_create: null CSR arrays");
     SSL_CHECK_ARG(n_rows >= 0 && n_cols > 0 && nnz >= 0 && nnz < (int64_t)INT32_MAX, "ssl_plan_create: bad sizes");
@@ -234,7 +234,11 @@ extern "C" int ssl_plan_create(ssl_plan **out, const int32_t *h_rowptr, const in
     // ---- host work list: split long rows, then whole rows by descending degree (counting sort) ----
     std::vector<int4> items;
     std::vector<int2> longs;
-    std::vector<int64_t> bucket(kMinSeg + 2, 0);
+    // two sides (rows before / from side_split), each ordered by descending degree: bucket index = side * (kMinSeg+1) + (kMinSeg - deg)
+    const int64_t local_split = std::min<int64_t>(std::max<int64_t>(side_split - row_offset, 0), n_rows);
+    const int n_bucket = 2 * (kMinSeg + 1);
+    std::vector<int64_t> bucket(n_bucket + 1, 0);
+    auto bucket_of = [&](int64_t r, int64_t deg) { return (int)((r < local_split ? 0 : 1) * (kMinSeg + 1) + (kMinSeg - deg)); };
     int64_t max_deg = 0;
     for (int64_t r = 0; r < n_rows; ++r) {
         const int64_t deg = (int64_t)h_rowptr[r + 1] - h_rowptr[r];
@@ -251,23 +255,23 @@ extern "C" int ssl_plan_create(ssl_plan **out, const int32_t *h_rowptr, const in
                 items.push_back(make_int4((int)r, (int)b, (int)std::min<int64_t>(b + seg, h_rowptr[r + 1]), (int)longs.size() - 1));
             }
         } else {
-            bucket[deg + 1]++;
+            bucket[bucket_of(r, deg)]++;
         }
     }
     const int64_t n_slots = (int64_t)items.size();
-    // descending-degree placement of the whole rows
-    std::vector<int64_t> start(kMinSeg + 2, 0);
+    // counting-sort placement of the whole rows: side 0 by descending degree, then side 1 by descending degree
+    std::vector<int64_t> start(n_bucket, 0);
     {
         int64_t pos = n_slots;
-        for (int d = kMinSeg; d >= 0; --d) {
-            start[d] = pos;
-            pos += bucket[d + 1];
+        for (int b = 0; b < n_bucket; ++b) {
+            start[b] = pos;
+            pos += bucket[b];
         }
         items.resize(pos);
     }
     for (int64_t r = 0; r < n_rows; ++r) {
         const int64_t deg = (int64_t)h_rowptr[r + 1] - h_rowptr[r];
-        if (deg <= kMinSeg) items[start[deg]++] = make_int4((int)r, h_rowptr[r], h_rowptr[r + 1], -1);
+        if (deg <= kMinSeg) items[start[bucket_of(r, deg)]++] = make_int4((int)r, h_rowptr[r], h_rowptr[r + 1], -1);
     }
 
     ssl_plan *p = new (std::nothrow) ssl_plan();

@@ -25,7 +25,7 @@ class GraphPlan:
     reference's COO order (aug_utils.py:25-30) can be injected.
     """
 
-    def __init__(self, rows, cols, vals, n: int, device: torch.device, row_range=None, need_rev: bool = False):
+    def __init__(self, rows, cols, vals, n: int, device: torch.device, row_range=None, need_rev: bool = False, side_split: int = 0):
         rows = _np(rows).astype(np.int64)
         cols = _np(cols).astype(np.int64)
         vals = _np(vals).astype(np.float32)
@@ -64,15 +64,15 @@ class GraphPlan:
             _lib.check(_lib.lib.ssl_plan_create(
                 C.byref(self._handle), self.h_rowptr.ctypes.data, self.colidx.data_ptr(), self.vals.data_ptr(),
                 self.rev.data_ptr() if self.rev is not None else None,
-                self.n_rows, self.n, self.nnz, self.row_offset, stream), 'ssl_plan_create')
+                self.n_rows, self.n, self.nnz, self.row_offset, int(side_split), stream), 'ssl_plan_create')
 
     @classmethod
-    def from_torch_adj(cls, adj: torch.Tensor, device=None, need_rev: bool = False) -> 'GraphPlan':
-        """From the reference's sparse COO tensor (any device)."""
+    def from_torch_adj(cls, adj: torch.Tensor, device=None, need_rev: bool = False, side_split: int = 0) -> 'GraphPlan':
+        """From the reference's sparse COO tensor (any device).  side_split = |U| orders the work list side by side."""
         idx = adj._indices() if adj.layout == torch.sparse_coo else adj.to_sparse_coo()._indices()
         val = adj._values() if adj.layout == torch.sparse_coo else adj.to_sparse_coo()._values()
         device = device if device is not None else adj.device
-        return cls(idx[0].cpu().numpy(), idx[1].cpu().numpy(), val.cpu().numpy(), adj.shape[0], device, need_rev=need_rev)
+        return cls(idx[0].cpu().numpy(), idx[1].cpu().numpy(), val.cpu().numpy(), adj.shape[0], device, need_rev=need_rev, side_split=side_split)
 
     @property
     def handle(self):

@@ -40,10 +40,10 @@ class RowShard:
     def n_local(self) -> int:
         return self.r1 - self.r0
 
-    def make_plan(self, adj: torch.Tensor, device) -> GraphPlan:
+    def make_plan(self, adj: torch.Tensor, device, side_split: int = 0) -> GraphPlan:
         idx, val = adj._indices(), adj._values()
         return GraphPlan(idx[0].cpu().numpy(), idx[1].cpu().numpy(), val.cpu().numpy(), adj.shape[0], device,
-                         row_range=(self.r0, self.r1))
+                         row_range=(self.r0, self.r1), side_split=side_split)
 
     def alloc_rows(self, *tail, device, dtype=torch.float32) -> torch.Tensor:
         """Local output buffer with ``block`` rows (>= n_local) so it can be all-gathered in place."""
