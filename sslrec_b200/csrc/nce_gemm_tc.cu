@@ -26,6 +26,10 @@
 //                     (TMEM lane = row, one 32-column half of the tile).  tcgen05.ld S (which frees the S
 //                     buffer for the next GEMM1 at once), ex2, row sums in registers, tf32 split of E,
 //                     tcgen05.st E_hi / E_lo into their own TMEM buffers; finally O is read out once per CTA.
+//   Roofline: 65536 MACs per K=8 MMA at the measured tf32 peak (cuBLAS bf16 burst / 2 = 865 TFLOP/s) is ~44 SM cycles,
+//   48 MMAs per 64-column tile = ~2100 cycles; measured 2350 cycles per tile at the bench's forward shape
+//   (0.339 ms, 777 TFLOP/s of tf32 MMA work = 90 % of that peak).  Tried and dropped: the resident operand's
+//   hi part in TMEM (TS-form GEMM1, single S buffer) -- same speed, slower backward shape.
 //   TMEM columns    : [0,128) S x2, [128,256) E_hi x2, [256,384) E_lo x2, [384,384+d) O (hi*hi),
 //                     [448,448+d) O correction terms -- all 512 columns.
 #include <cuda.h>
