@@ -38,6 +38,7 @@ WORKLOADS = {
     'lightgcn-gowalla': ('lightgcn', 'gowalla', dict(layer_num=3, embedding_size=64, reg_weight=1.0e-8, keep_rate=0.5)),
     'sgl-yelp': ('sgl', 'yelp', dict(layer_num=3, embedding_size=64, temperature=0.2, cl_weight=1.0, reg_weight=1.0e-5,
                                      keep_rate=0.5, augmentation='edge_drop')),
+    'lightgcn-xl-8th': ('lightgcn', 'synthetic-xl-8th', dict(layer_num=3, embedding_size=128, reg_weight=1.0e-8, keep_rate=1.0)),
     'ncl-amazon': ('ncl', 'amazon', dict(layer_num=3, embedding_size=64, high_order=2, reg_weight=1.0e-7, proto_weight=1.0e-4,
                                          struct_weight=1.0e-3, temperature=0.1, epoch_period=3, cluster_num=50, keep_rate=1.0)),
     'hccf-amazon': ('hccf', 'amazon', dict(layer_num=2, embedding_size=64, reg_weight=1.0e-7, cl_weight=1.0, temperature=0.1,

@@ -12,16 +12,29 @@ SHAPES = {
     'yelp': (42712, 26822, 182357),
     'amazon': (76469, 83761, 966680),
     'synthetic-xl': (10_000_000, 2_000_000, 300_000_000),
+    'synthetic-xl-8th': (1_250_000, 250_000, 37_500_000),      # one GPU's eighth of config 4 (same degree statistics)
 }
 # item-popularity exponent: 0.5 reproduces the bundled datasets' head (max item degree ~1e3 at
 # amazon's size; the real matrices have 841 / 309 / 1018); 1.0 is BASELINE.json config 4's generator
-ZIPF = {'gowalla': 0.5, 'yelp': 0.5, 'amazon': 0.5, 'synthetic-xl': 1.0}
+ZIPF = {'gowalla': 0.5, 'yelp': 0.5, 'amazon': 0.5, 'synthetic-xl': 1.0, 'synthetic-xl-8th': 1.0}
 
 
 def named_graph(name: str, seed: int = 2023):
     n_user, n_item, n_edge = SHAPES[name]
     rows, cols = bipartite_graph(n_user, n_item, n_edge, seed, ZIPF[name])
     return rows, cols, n_user, n_item
+
+
+def _merge_unique(keys: np.ndarray, new: np.ndarray) -> np.ndarray:
+    """sorted-unique union of a sorted-unique array with arbitrary new values (one sort of ``new`` only)."""
+    new.sort()
+    if new.size:
+        new = new[np.concatenate([[True], new[1:] != new[:-1]])]
+    if keys.size == 0:
+        return new
+    pos = np.searchsorted(keys, new)
+    fresh = (pos == keys.size) | (keys[np.minimum(pos, keys.size - 1)] != new)
+    return np.insert(keys, pos[fresh], new[fresh])
 
 
 def bipartite_graph(n_user: int, n_item: int, n_edge: int, seed: int = 2023, zipf_alpha: float = 1.0):
@@ -35,17 +48,21 @@ def bipartite_graph(n_user: int, n_item: int, n_edge: int, seed: int = 2023, zip
     perm = rng.permutation(n_item)
     keys = np.empty(0, dtype=np.int64)
     want = deg.copy()
-    for _ in range(64):
+    for it in range(12):
         users = np.repeat(np.arange(n_user, dtype=np.int64), want)
-        items = perm[np.searchsorted(cdf, rng.random(users.shape[0]), side='right').clip(0, n_item - 1)]
-        keys = np.unique(np.concatenate([keys, users * n_item + items]))
+        if it < 2:          # popularity-driven draws; later passes fill the collision losses uniformly
+            items = perm[np.searchsorted(cdf, rng.random(users.shape[0]), side='right').clip(0, n_item - 1)]
+        else:
+            items = rng.integers(0, n_item, size=users.shape[0], dtype=np.int64)
+        keys = _merge_unique(keys, users * n_item + items)
         if keys.shape[0] >= n_edge:
             break
         missing = n_edge - keys.shape[0]
         have = np.bincount(keys // n_item, minlength=n_user)
         want = np.maximum(deg - have, 0)
-        if want.sum() < missing:        # top up uniformly when the per-user targets are exhausted by collisions
-            want = want + rng.multinomial(int((missing - want.sum()) * 1.1) + 1, np.full(n_user, 1.0 / n_user))
+        short = missing - int(want.sum())
+        if short > 0:       # rounding of the degree targets: spread the remainder over random users
+            want = want + np.bincount(rng.integers(0, n_user, size=int(short * 1.05) + 1), minlength=n_user)
     if keys.shape[0] > n_edge:
         keys = np.sort(rng.choice(keys, size=n_edge, replace=False))
     if keys.shape[0] != n_edge:

@@ -33,13 +33,16 @@ class GraphPlan:
         self.device = torch.device(device)
         r0, r1 = (0, self.n) if row_range is None else (int(row_range[0]), int(row_range[1]))
         self.row_offset, self.n_rows = r0, r1 - r0
+        if row_range is not None:                              # a shard sorts only its own entries
+            sel = (rows >= r0) & (rows < r1)
+            rows, cols, vals = rows[sel], cols[sel], vals[sel]
         order = np.lexsort((cols, rows))                       # CSR order: row, then col
-        self.coo_to_csr_full = np.empty_like(order)
-        self.coo_to_csr_full[order] = np.arange(order.shape[0])
+        if row_range is None:
+            self.coo_to_csr_full = np.empty_like(order)
+            self.coo_to_csr_full[order] = np.arange(order.shape[0])
         rows_s, cols_s, vals_s = rows[order], cols[order], vals[order]
-        lo, hi = np.searchsorted(rows_s, r0), np.searchsorted(rows_s, r1)
-        self.entry_lo = int(lo)
-        rows_l, cols_l, vals_l = rows_s[lo:hi] - r0, cols_s[lo:hi], vals_s[lo:hi]
+        self.entry_lo = 0
+        rows_l, cols_l, vals_l = rows_s - r0, cols_s, vals_s
         self.nnz = int(rows_l.shape[0])
         rowptr = np.zeros(self.n_rows + 1, dtype=np.int64)
         rowptr[1:] = np.cumsum(np.bincount(rows_l, minlength=self.n_rows))
@@ -86,6 +89,8 @@ class GraphPlan:
     def mask_to_csr(self, mask_in_caller_order) -> torch.Tensor:
         """uint8 keep-mask given in the order of the COO triplets passed to the constructor ->
         device uint8 tensor in CSR entry order (what edge_mode 2 reads)."""
+        if not hasattr(self, 'coo_to_csr_full'):
+            raise ValueError('injected masks are a single-GPU debugging aid (row-sharded plans keep no COO map)')
         m = _np(mask_in_caller_order).astype(np.uint8)
         out = np.empty_like(m)
         out[self.coo_to_csr_full] = m
