@@ -58,6 +58,7 @@ __global__ void __launch_bounds__(kThreads, (V <= 3) ? 4 : 3) prop_kernel(PlanDe
     constexpr bool SHARED = MODE == 0;
     constexpr int NA = SHARED ? 1 : V;
     constexpr int NW = (MODE == 2) ? V : 1;        // distinct weights per entry
+    constexpr int UNR = (NA == 1 && G >= 8) ? 8 : 4;   // entries whose row gathers are in flight together (single-view: 8)
     const int lane = threadIdx.x & 31;
     const int gl = lane % G;
     const int grp = lane / G;
@@ -101,18 +102,18 @@ __global__ void __launch_bounds__(kThreads, (V <= 3) ? 4 : 3) prop_kernel(PlanDe
             wv[v] = f;
         }
         const int cnt = min(G, it.z - base);
-        for (int j = 0; j < cnt; j += 4) {
-            int cj[4];
-            float wj[4][NW];
-            float4 x[4][NA];
+        for (int j = 0; j < cnt; j += UNR) {
+            int cj[UNR];
+            float wj[UNR][NW];
+            float4 x[UNR][NA];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < UNR; ++u) {
                 cj[u] = __shfl_sync(gmask, c, j + u, G);
 #pragma unroll
                 for (int v = 0; v < NW; ++v) wj[u][v] = __shfl_sync(gmask, wv[v], j + u, G);
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < UNR; ++u) {
                 const float *xr = a.x_in + (size_t)cj[u] * in_row + col;
 #pragma unroll
                 for (int v = 0; v < NA; ++v) {
@@ -121,7 +122,7 @@ __global__ void __launch_bounds__(kThreads, (V <= 3) ? 4 : 3) prop_kernel(PlanDe
                 }
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
+            for (int u = 0; u < UNR; ++u)
 #pragma unroll
                 for (int v = 0; v < NA; ++v) ssl::fma4(acc[v], wj[u][NW == 1 ? 0 : v], x[u][v]);
         }
