@@ -153,7 +153,7 @@ def cpu_steps(model, hp, rows, cols, n_user, n_item, batches, budget_s, max_step
     # untimed step per candidate doubles as the warm-up
     cands = sorted({os.cpu_count() or 1, min(os.cpu_count() or 1, 32)}, reverse=True)
     best, threads = None, cands[0]
-    for c in cands[:max(1, warmup + 1)]:
+    for c in cands:
         torch.set_num_threads(c)
         t0 = time.perf_counter()
         tr.step(tb[0])
