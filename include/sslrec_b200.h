@@ -184,7 +184,9 @@ SSL_API int ssl_softmax_gemm(const float *R, int64_t n_r, const float *C, const 
 /* The same contraction on the tcgen05 tensor cores with 3xTF32 error compensation (fp32-grade
  * accuracy): operands are the hi / lo splits written by ssl_rows_normalize, row-major [n, dim],
  * and for the streamed operand also the transposed splits CT_hi / CT_lo [dim, ct_pitch];
- * dim must be 32 or 64.  Outputs and semantics are those of ssl_softmax_gemm. */
+ * dim must be 32 or 64.  colscale, when given, must be readable up to ceil64(n_c) floats (the
+ * padded tail is loaded with the tile and masked).  Outputs and semantics are those of
+ * ssl_softmax_gemm. */
 SSL_API int ssl_softmax_gemm_tf32x3(const float *R_hi, const float *R_lo, int64_t n_r, const float *C_hi, const float *C_lo,
                             const float *CT_hi, const float *CT_lo, int64_t ct_pitch, int64_t n_c, int32_t dim,
                             const float *colscale, float offset, int32_t n_split, float *rowsum_part, float *o_part,

@@ -667,7 +667,7 @@ def _nce_bwd(saved, g):
                                        idx.data_ptr(), B, d, tau, g.data_ptr(), scale, g1, e1.stride, g2, e2.stride, s),
                   'ssl_nce_bwd_rows')
         if gt is not None and n > 0:
-            colscale = torch.empty(ceil_to(B, 64), **f)
+            colscale = torch.zeros(ceil_to(B, 64), **f)   # padded tail is read (then masked) by the tile loads
             check(lib.ssl_nce_colscale(rowsum.data_ptr(), B, g.data_ptr(), scale, colscale.data_ptr(), s), 'ssl_nce_colscale')
             n_split = choose_split((n + 127) // 128, ceil_to(B, 64) // 64, slots=148 if tc else 296, prefer_few=bool(tc))
             dt_part = torch.empty(n_split, n, d, **f)
