@@ -24,9 +24,10 @@ def init_seed():
 
 
 class Trainer(object):
-    def __init__(self, data_handler, logger=None):
+    def __init__(self, data_handler, logger=None, grad_sync=None):
         self.data_handler = data_handler
         self.logger = logger
+        self.grad_sync = grad_sync     # parallel.BatchShard: data-parallel ranks average gradients before the step
 
     def create_optimizer(self, model):
         optim_config = configs['optimizer']
@@ -42,6 +43,8 @@ class Trainer(object):
         the copy has landed (one step later), so the host keeps enqueueing while the GPU works."""
         train_dataloader = self.data_handler.train_dataloader
         train_dataloader.dataset.sample_negs()
+        if hasattr(train_dataloader.sampler, 'set_epoch'):
+            train_dataloader.sampler.set_epoch(epoch_idx)
         loss_log_dict = {}
         ep_loss = 0
         model.train()
@@ -51,6 +54,8 @@ class Trainer(object):
             batch_data = list(map(lambda x: x.long().to(configs['device'], non_blocking=True), tem))
             loss, loss_dict = model.cal_loss(batch_data)
             loss.backward()
+            if self.grad_sync is not None:
+                self.grad_sync.average_gradients(model.parameters())
             self.optimizer.step()
             for done in reader.push(loss, loss_dict):
                 ep_loss += done[0]

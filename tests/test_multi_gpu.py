@@ -59,6 +59,84 @@ def test_row_shard_plumbing_gloo_world2(n):
     mp.spawn(_gloo_worker, args=(2, _free_port(), n), nprocs=2, join=True)
 
 
+def _dp_gloo_worker(rank, world, port):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from sslrec_b200.parallel import BatchShard
+    sync = BatchShard(dist, rank, world)
+    # two parameters whose gradients are the halves of one flat sink (the embedding table) + a separate one
+    flat = torch.arange(12, dtype=torch.float32).view(6, 2) * (rank + 1)
+    pu, pi, pw = (torch.nn.Parameter(torch.zeros(4, 2)), torch.nn.Parameter(torch.zeros(2, 2)), torch.nn.Parameter(torch.zeros(3)))
+    pu.grad, pi.grad, pw.grad = flat[:4], flat[4:], torch.full((3,), float(rank))
+    bufs = sync.coalesce([pi.grad, pw.grad, pu.grad])
+    assert sorted(b.numel() for b in bufs) == [3, 12]            # the adjacent halves travel as one buffer
+    sync.average_gradients([pu, pi, pw, torch.nn.Parameter(torch.zeros(1))])   # a parameter without .grad is skipped
+    want = torch.arange(12, dtype=torch.float32).view(6, 2) * (sum(range(1, world + 1)) / world)
+    assert torch.equal(flat, want) and torch.equal(pu.grad, want[:4]) and torch.equal(pi.grad, want[4:])
+    assert torch.allclose(pw.grad, torch.full((3,), (world - 1) / 2.0))
+    # the loader gives every rank a disjoint share of each epoch
+    ds = torch.utils.data.TensorDataset(torch.arange(20))
+    loader = sync.shard_loader(ds, batch_size=4, seed=7)
+    loader.sampler.set_epoch(3)
+    mine = torch.cat([b[0] for b in loader])
+    seen = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(seen, mine)
+    assert sorted(torch.cat(seen).tolist()) == list(range(20))
+    dist.destroy_process_group()
+
+
+def test_batch_shard_gradient_average_gloo_world2():
+    mp.spawn(_dp_gloo_worker, args=(2, _free_port()), nprocs=2, join=True)
+
+
+def _dp_gpu_worker(rank, world, port, out):
+    """Data-parallel step (one batch per rank, averaged gradients) == the single-GPU step on the concatenated batch."""
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests'))
+    import ssl_test_helpers as H
+    from oracle import inputs, replay
+    from sslrec_b200.optim import FusedAdam
+    from sslrec_b200.parallel import BatchShard
+    for name in ('simgcl', 'lightgcn'):
+        g = replay.load_golden(name, 'small')
+        case = inputs.make_case('small')
+        full = [torch.from_numpy(case[k]).cuda() for k in ('ancs', 'poss', 'negs')]
+        half = full[0].numel() // world
+        out = {}
+        for dp in (False, True):
+            model, _ = H.make_model(name, case, g['hp'], device=f'cuda:{rank}')
+            model.load_state_dict({'user_embeds': case['user_e'], 'item_embeds': case['item_e']})
+            opt = FusedAdam(model.parameters(), lr=1e-2)
+            batch = [t[rank * half:(rank + 1) * half] for t in full] if dp else [t[:world * half] for t in full]
+            loss, _ = model.cal_loss(batch)
+            loss.backward()
+            if dp:
+                BatchShard(dist, rank, world).average_gradients(model.parameters())
+                dist.all_reduce(loss, op=dist.ReduceOp.AVG)
+            grads = (model.user_embeds.grad.clone(), model.item_embeds.grad.clone())
+            opt.step()
+            out[dp] = (loss.item(), grads, model.user_embeds.detach().clone(), model.item_embeds.detach().clone())
+        assert abs(out[True][0] - out[False][0]) <= 2e-6 * max(1.0, abs(out[False][0])), name
+        for a, b in zip(out[True][1], out[False][1]):
+            assert torch.allclose(a, b, rtol=1e-4, atol=1e-7 + 2e-5 * b.abs().max().item()), name
+        # identical parameters on every rank after the step
+        for p in out[True][2:]:
+            ref = p.clone()
+            dist.broadcast(ref, src=0)
+            assert torch.equal(p, ref), name
+    dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_data_parallel_step_matches_big_batch():
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs (run with gpurun --gpus 2)')
+    mp.spawn(_dp_gpu_worker, args=(2, _free_port(), None), nprocs=2, join=True)
+
+
 def _gpu_worker(rank, world, port, out):
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
