@@ -161,9 +161,9 @@ def cpu_steps(model, hp, rows, cols, n_user, n_item, batches, budget_s, max_step
     tr = O.CpuTrainer(model, adj, hp['embedding_size'], dict(hp, lr=1e-3))
     tb = [tuple(torch.from_numpy(b[i]) for i in range(3)) for b in batches]
     t_start = time.perf_counter()
-    # all host threads, unless fewer are faster (torch's sparse COO addmm stops scaling early): one
+    # all usable host threads (affinity capped by the cgroup quota), unless 32 are faster (torch's sparse COO addmm stops scaling early): one
     # untimed step per candidate doubles as the warm-up
-    cands = sorted({os.cpu_count() or 1, min(os.cpu_count() or 1, 32), usable_cpus()}, reverse=True)
+    cands = sorted({usable_cpus(), min(usable_cpus(), 32)}, reverse=True)
     best, threads = None, cands[0]
     for c in cands:
         torch.set_num_threads(c)
@@ -300,7 +300,7 @@ def run_ours(args):
 
     def step_resident(i):
         opt.zero_grad()
-        b = dev_batches[i]
+        b = dev_batches[i % len(dev_batches)]
         loss, parts = model.cal_loss(as_batch(b))
         loss.backward()
         if sync is not None:
@@ -317,7 +317,7 @@ def run_ours(args):
         """The loop of sslrec_b200.trainer.Trainer.train_epoch: H2D of the batch, cal_loss, backward, step, and the
         step's loss scalars copied device -> pinned host asynchronously (read one step later)."""
         opt.zero_grad()
-        b = host_batches[i].to(dev, non_blocking=True)
+        b = host_batches[i % len(host_batches)].to(dev, non_blocking=True)
         loss, parts = model.cal_loss(as_batch(b))
         loss.backward()
         if sync is not None:
@@ -329,7 +329,7 @@ def run_ours(args):
 
     def step_e2e(i):
         opt.zero_grad()
-        b = host_batches[i].to(dev, non_blocking=True)           # trainer.py:64
+        b = host_batches[i % len(host_batches)].to(dev, non_blocking=True)           # trainer.py:64
         loss, parts = model.cal_loss(as_batch(b))
         v = loss.item()                                          # trainer.py:66 (D2H sync)
         loss.backward()
@@ -392,7 +392,7 @@ def run_ours(args):
     # (r01: a pass read 8.7 ms/step where its neighbours read 2.9 ms with identical kernels, see profiles/r01d_*).
     passes = [timed(step_resident, no_sampling=True) for _ in range(3)]
     ms_res, launches, _ = min(passes, key=lambda p: p[0])
-    ms_res_sampled, _, clocks = timed(step_resident)
+    ms_res_sampled, _, clocks = timed(step_resident, steps=max(K, 60))      # long enough for several NVML samples
     if clocks is not None:
         clocks['sampled_replay_ms_per_step'] = ms_res_sampled
     # e2e is timed WITHOUT clock sampling (one NVML sample costs ~14 ms of host time, which the per-step
