@@ -426,6 +426,28 @@ def run_ours(args):
             dist.destroy_process_group()
         return
 
+    # ---- one real epoch through Trainer.train_epoch (sample_negs + loader + loop), device loader vs host DataLoader ----
+    epoch = None
+    if world == 1 and model_name != 'ncl' and len(rows) // BATCH <= 1000:
+        import types
+        from sslrec_b200.data_handler import DeviceLoader, DeviceTrnData
+        from sslrec_b200.trainer import Trainer
+        epoch = {'batches': (len(rows) + BATCH - 1) // BATCH,
+                 'how': 'wall clock of Trainer.train_epoch (negative sampling, shuffling, batching, H2D, steps, loss reads), after one warm-up epoch'}
+        for key, loader in (('device_loader', DeviceLoader(DeviceTrnData(trn, dev, 2023), BATCH)), ('host_dataloader', dh.train_dataloader)):
+            tr = Trainer(types.SimpleNamespace(train_dataloader=loader))
+            tr.optimizer = opt
+            best = None
+            for rep in range(3 if key == 'device_loader' else 2):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                tr.train_epoch(model, rep)
+                torch.cuda.synchronize()
+                dt = time.perf_counter() - t0
+                best = dt if (best is None or rep == 1) else min(best, dt)      # rep 0 is the warm-up
+            epoch[key + '_steps_per_sec'] = len(loader) / best
+            epoch[key + '_epoch_s'] = best
+
     peaks, peak_kind = measured_peaks()
     N, nnz, d = n_user + n_item, 2 * len(rows), hp['embedding_size']
     L = hp['layer_num']
@@ -498,6 +520,7 @@ def run_ours(args):
                        'loss + loss terms copied D2H asynchronously and read one step later (all reads drained inside the timed region)'},
         'e2e_strict_sync': {'value': units * 1e3 / ms_e2e_strict, 'unit': 'steps/s', 'ms_per_step': ms_e2e_strict,
                             'how': 'the reference trainer\'s blocking reads: loss.item() after cal_loss and float(v) per loss term (trainer.py:66,72)'},
+        'e2e_epoch': epoch,
         'gpu_launches': launches, 'gpu_launches_per_step': launches / K,
         'embeddings_propagated_per_sec': emb_per_step * value,
         'roofline': roofline, 'roofline_infonce': roofline_nce, 'cpu_baseline': cpu,

@@ -240,6 +240,26 @@ SSL_API int ssl_predict_mask(const float *users_tab, int64_t u_stride, const flo
                      const int32_t *trn_rowptr, const int32_t *trn_cols, float *preds, void *stream);
 SSL_API int ssl_topk(const float *preds, int64_t n_b, int64_t n_item, int32_t k, int64_t *out_idx, float *out_val, void *stream);
 
+/* ------------------------------------------------------------------------------------------
+ * a17  KMeansClustering (aug_utils.py:142-157, NCL): one Lloyd iteration = assignment
+ *   idx[r] = argmin_k sum_j (x_rj - c_kj)^2 (ties -> lowest k) and the centroid update
+ *   c_k = sum_{idx[r]=k} x_r / (count_k + 1e-6), in place.  Deterministic (static row partition,
+ *   ordered partial sums, no floating-point atomics).  ssl_kmeans_workspace gives the launch
+ *   shape: part_sum must hold n_cta * k * dim floats and part_cnt n_cta * k.  *changed is
+ *   incremented by the number of rows whose assignment changed (initialise assign to -1).
+ * ------------------------------------------------------------------------------------------ */
+SSL_API int ssl_kmeans_workspace(int64_t n, int32_t dim, int32_t k, int32_t *n_cta, int32_t *n_warps);
+SSL_API int ssl_kmeans_iter(const float *x, int64_t stride, int64_t n, int32_t dim, int32_t k, float *centroids, int64_t *assign,
+                    float *part_sum, float *part_cnt, float *counts, int32_t *changed, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a21  PairwiseTrnData.sample_negs (datasets_general_cf.py:13-26): negs[e] = an item drawn uniformly
+ *   until users[e] has no training interaction with it (membership by binary search in the sorted
+ *   training CSR, int32).  Counter-based: a pure function of (seed, epoch, e).
+ * ------------------------------------------------------------------------------------------ */
+SSL_API int ssl_sample_negs(const int64_t *users, int64_t n_pairs, const int32_t *trn_rowptr, const int32_t *trn_cols,
+                    int64_t n_item, uint64_t seed, uint32_t epoch, int64_t *negs, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -83,6 +83,89 @@ class PairwiseWEpochFlagTrnData(PairwiseTrnData):
         return anc, pos, neg, flag
 
 
+class DeviceTrnData:
+    """The training pairs and their per-epoch negatives resident on the device: ``sample_negs`` is one launch of
+    ``ssl_sample_negs`` (rejection sampling against the sorted training CSR; a pure function of seed, epoch and pair)
+    instead of the host loop of datasets_general_cf.py:13-26 followed by a host->device copy per batch."""
+
+    def __init__(self, coomat, device, seed: int = 2023, epoch_period=None):
+        from ._lib import check, lib                     # raises if the CUDA library is missing: no host fallback here
+        self._check, self._lib = check, lib
+        coomat = sp.coo_matrix(coomat)
+        self.device = torch.device(device)
+        if self.device.type != 'cuda':
+            raise RuntimeError('DeviceTrnData needs a CUDA device (use PairwiseTrnData + DataLoader on the host)')
+        csr = sp.csr_matrix((np.ones(coomat.nnz, dtype=np.float32), (coomat.row, coomat.col)), shape=coomat.shape)
+        csr.sum_duplicates()
+        csr.sort_indices()
+        self.n_item = coomat.shape[1]
+        self.rows = torch.from_numpy(coomat.row.astype(np.int64)).to(self.device)
+        self.cols = torch.from_numpy(coomat.col.astype(np.int64)).to(self.device)
+        self.negs = torch.zeros_like(self.rows)
+        self._rowptr = torch.from_numpy(csr.indptr.astype(np.int32)).to(self.device)
+        self._csr_cols = torch.from_numpy(csr.indices.astype(np.int32)).to(self.device)
+        self.seed, self.epoch = int(seed), 0
+        self.epoch_period = epoch_period                 # NCL: pairwise_with_epoch_flag (datasets_general_cf.py:28-44)
+        self.epoch_flag_counter = -1
+
+    def sample_negs(self):
+        with torch.cuda.device(self.device):
+            self._check(self._lib.ssl_sample_negs(self.rows.data_ptr(), self.rows.numel(), self._rowptr.data_ptr(),
+                                                  self._csr_cols.data_ptr(), self.n_item, self.seed, self.epoch, self.negs.data_ptr(),
+                                                  torch.cuda.current_stream(self.device).cuda_stream), 'ssl_sample_negs')
+        self.epoch += 1
+
+    def __len__(self):
+        return self.rows.numel()
+
+    def batch(self, idx: torch.Tensor, has_pair0: bool = False):
+        """``has_pair0``: the batch contains training pair 0 (the loader knows; no device sync here)."""
+        out = [self.rows[idx], self.cols[idx], self.negs[idx]]
+        if self.epoch_period is not None:
+            # the flag of datasets_general_cf.py:35-44: 1 on the very first sample served, and on sample 0 once
+            # every ``epoch_period`` visits of it
+            flags = torch.zeros_like(idx)
+            if self.epoch_flag_counter == -1:
+                flags[0] = 1
+                self.epoch_flag_counter = 0
+            if has_pair0:
+                self.epoch_flag_counter += 1
+                if self.epoch_flag_counter % self.epoch_period == 0:
+                    flags = flags | (idx == 0).long()
+            out.append(flags)
+        return out
+
+
+class DeviceLoader:
+    """``DataLoader(trn_data, batch_size, shuffle=True)`` (data_handler_general_cf.py:95) for a DeviceTrnData: a fresh
+    device permutation per epoch, batches gathered on the device.  ``rank`` / ``world`` give each data-parallel
+    rank a disjoint share of the same permutation (every rank seeds the same generator)."""
+
+    def __init__(self, dataset: DeviceTrnData, batch_size: int, rank: int = 0, world: int = 1, seed: int = 2023):
+        self.dataset, self.batch_size, self.rank, self.world = dataset, int(batch_size), rank, world
+        self.sampler = None
+        self._gen = torch.Generator(device=dataset.device)
+        self._gen.manual_seed(seed)
+
+    def _share(self) -> int:
+        return (len(self.dataset) + self.world - 1) // self.world
+
+    def __len__(self):
+        return (self._share() + self.batch_size - 1) // self.batch_size
+
+    def __iter__(self):
+        perm = torch.randperm(len(self.dataset), device=self.dataset.device, generator=self._gen)
+        if self.world > 1:
+            share = self._share()
+            perm = torch.cat([perm, perm[:share * self.world - perm.numel()]])[self.rank::self.world]   # padded like DistributedSampler
+        at0 = -1
+        if self.dataset.epoch_period is not None:            # one read per epoch: where pair 0 landed in this rank's share
+            hit = (perm == 0).nonzero()
+            at0 = int(hit[0]) if hit.numel() else -1
+        for lo in range(0, perm.numel(), self.batch_size):
+            yield self.dataset.batch(perm[lo:lo + self.batch_size], lo <= at0 < lo + self.batch_size)
+
+
 class AllRankTstData(data.Dataset):
     """Test users with their held-out positives and a dense train-mask row (datasets_general_cf.py:46-68)."""
 
@@ -133,7 +216,13 @@ class DataHandlerGeneralCF:
             trn_data = PairwiseWEpochFlagTrnData(trn_mat)
         else:
             raise NotImplementedError(configs['train']['loss'])
-        self.train_dataloader = data.DataLoader(trn_data, batch_size=configs['train']['batch_size'], shuffle=True, num_workers=0)
+        if configs['train'].get('device_loader', False):
+            # optional key: pairs, negative sampling and batching on the device (no per-sample host collate, no H2D per batch)
+            period = configs['model']['epoch_period'] if configs['train']['loss'] == 'pairwise_with_epoch_flag' else None
+            seed = configs['train'].get('seed', 2023)
+            self.train_dataloader = DeviceLoader(DeviceTrnData(trn_mat, configs['device'], seed, period), configs['train']['batch_size'], seed=seed)
+        else:
+            self.train_dataloader = data.DataLoader(trn_data, batch_size=configs['train']['batch_size'], shuffle=True, num_workers=0)
         dense = configs['test'].get('dense_mask', True)      # optional key: False = mask on device from the training CSR
         if val_mat is not None:
             self.valid_dataloader = data.DataLoader(AllRankTstData(val_mat, trn_mat, dense), batch_size=configs['test']['batch_size'], shuffle=False, num_workers=0)

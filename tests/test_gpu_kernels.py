@@ -232,3 +232,145 @@ def test_c_abi_rejects_bad_arguments():
     x = torch.zeros(8, device='cuda')
     rc = _lib.lib.ssl_rows_normalize(x.data_ptr(), 6, None, 1, 6, 0, 1.0, x.data_ptr(), None, None, None, None, None, None, 0, None)
     assert rc == -1                                               # dim must be a multiple of 4
+
+
+# ---------------------------------------------------------------------------------------------------
+# in-kernel counter-based draws, bit for bit against their numpy restatement (oracle/philox.py)
+# ---------------------------------------------------------------------------------------------------
+
+def _apply_layer(prop, plan_n, dim, v, transpose, layer=1):
+    a = prop._args(dim, layer, transpose)
+    out = torch.empty(plan_n, 1, dim, device='cuda')
+    a.in_views, a.x_in, a.x_out = 1, v.data_ptr(), out.data_ptr()
+    prop._launch(a, v)
+    return out.view(plan_n, dim)
+
+
+@pytest.mark.parametrize('keep', [0.5, 0.9])
+def test_rng_edge_mask_equals_numpy_philox_mask(keep):
+    """edge_mode 1 (keep test evaluated in-kernel from Philox(seed; row, col, stream)) gives exactly the SpMM of
+    edge_mode 2 with the mask computed on the host from the same generator, forward and transposed."""
+    from oracle import philox as P
+    from sslrec_b200 import engine as E
+    adj = _graph(800, 600, 9000, 18, 400)
+    plan = _plan(adj, need_rev=True)
+    seed = 0x1234_5678_9ABC_DEF1
+    mask = P.edge_keep(seed, 0, adj.rows, adj.cols, keep)
+    assert abs(mask.mean() - keep) < 0.02
+    x = torch.randn(adj.n, 64, generator=torch.Generator().manual_seed(14)).cuda()
+    rng = E.Propagation(plan, [E.ViewSpec(edge_mode=1, keep=keep, scale=1.0 / keep, seed=seed)], 1)
+    inj = E.Propagation(plan, [E.ViewSpec(edge_mode=2, keep=keep, scale=1.0 / keep,
+                                          edge_masks=torch.from_numpy(mask.astype(np.uint8)).cuda())], 1)
+    for transpose in (False, True):
+        assert torch.equal(_apply_layer(rng, adj.n, 64, x, transpose), _apply_layer(inj, adj.n, 64, x, transpose)), transpose
+    # per-layer masks (HCCF) are keyed by the layer number
+    mask2 = P.edge_keep(seed, 2, adj.rows, adj.cols, keep)
+    rng2 = E.Propagation(plan, [E.ViewSpec(edge_mode=1, keep=keep, scale=1.0, seed=seed, per_layer_edges=True)], 2)
+    inj2 = E.Propagation(plan, [E.ViewSpec(edge_mode=2, keep=keep, scale=1.0, edge_masks=[None, torch.from_numpy(mask2.astype(np.uint8)).cuda()])], 2)
+    assert torch.equal(_apply_layer(rng2, adj.n, 64, x, False, layer=2), _apply_layer(inj2, adj.n, 64, x, False, layer=2))
+
+
+def test_rng_noise_and_node_masks_equal_numpy_philox():
+    from oracle import philox as P
+    from sslrec_b200 import engine as E
+    adj = _graph(300, 200, 3000, 19)
+    plan = _plan(adj)
+    seed, dim, L = 987654321012345, 48, 2
+    e0 = (torch.randn(adj.n, dim, generator=torch.Generator().manual_seed(15)) * 0.1).cuda()
+    us = [torch.from_numpy(P.noise_uniform(seed, layer, adj.n, dim)).cuda() for layer in range(1, L + 1)]
+    assert 0.45 < float(us[0].mean()) < 0.55 and float(us[0].max()) < 1.0
+    rng = E.Propagation(plan, [E.ViewSpec(noise_mode=1, seed=seed)], L, noise_eps=0.3).forward(e0, 300)
+    inj = E.Propagation(plan, [E.ViewSpec(noise_mode=2, noise_u=us)], L, noise_eps=0.3).forward(e0, 300)
+    assert torch.equal(rng.E, inj.E)
+    nm = P.node_keep(seed, np.arange(adj.n), 0.7)
+    assert abs(nm.mean() - 0.7) < 0.06
+    rng = E.Propagation(plan, [E.ViewSpec(node_mode=1, node_keep=0.7, seed=seed)], L).forward(e0, 300)
+    inj = E.Propagation(plan, [E.ViewSpec(node_mode=2, node_keep=0.7, node_mask=torch.from_numpy(nm.astype(np.uint8)).cuda())], L).forward(e0, 300)
+    assert torch.equal(rng.E, inj.E)
+
+
+@pytest.mark.parametrize('n_user,n_item,n_edge', [(300, 200, 3000), (50, 12, 400), (2000, 3000, 60000)])
+def test_negative_sampler_bit_exact_and_valid(n_user, n_item, n_edge):
+    """ssl_sample_negs == the numpy restatement on the same Philox draws; no negative is a training positive;
+    different epochs redraw; the draw is uniform over the items."""
+    import scipy.sparse as sp
+    from oracle import philox as P
+    from sslrec_b200.data_handler import DeviceLoader, DeviceTrnData
+    rows, cols = inputs.bipartite_edges(n_user, n_item, n_edge, 21)
+    mat = sp.coo_matrix((np.ones(len(rows), np.float32), (rows, cols)), shape=(n_user, n_item))
+    ds = DeviceTrnData(mat, 'cuda', seed=77)
+    csr = sp.csr_matrix(mat)
+    csr.sort_indices()
+    pos = set(zip(rows.tolist(), cols.tolist()))
+    got = []
+    for epoch in range(2):
+        ds.sample_negs()
+        negs = ds.negs.cpu().numpy()
+        want = P.sample_negs(mat.row, csr.indptr, csr.indices, n_item, 77, epoch)
+        assert np.array_equal(negs, want), epoch
+        assert negs.min() >= 0 and negs.max() < n_item
+        assert not any((int(u), int(j)) in pos for u, j in zip(mat.row, negs))
+        got.append(negs)
+    assert (got[0] != got[1]).mean() > 0.5
+    if n_edge >= 60000:            # uniform over the items the user has NOT interacted with: chi-square against the exact expectation
+        deg = np.diff(csr.indptr).astype(np.float64)
+        w = deg / (n_item - deg)                                   # pairs of user u x probability of each admissible item
+        exp = w.sum() - np.bincount(csr.indices, weights=np.repeat(w, np.diff(csr.indptr)), minlength=n_item)
+        cnt = np.bincount(got[0], minlength=n_item).astype(np.float64)
+        ok = exp >= 5
+        chi2, dof = ((cnt[ok] - exp[ok]) ** 2 / exp[ok]).sum(), int(ok.sum())
+        assert dof > 1000 and chi2 < dof + 6 * math.sqrt(2 * dof), (chi2, dof)
+    # one epoch of the device loader serves every pair exactly once, with its negative
+    loader = DeviceLoader(ds, 256, seed=5)
+    seen = torch.cat([torch.stack(b[:3], 1) for b in loader]).cpu().numpy()
+    assert len(loader) == (len(rows) + 255) // 256 and seen.shape == (len(rows), 3)
+    order = np.lexsort((seen[:, 1], seen[:, 0]))
+    ref = np.stack([mat.row, mat.col, got[1]], 1)
+    assert np.array_equal(seen[order], ref[np.lexsort((ref[:, 1], ref[:, 0]))])
+    # NCL's epoch flag (datasets_general_cf.py:35-44): the very first sample served, then pair 0 every epoch_period visits
+    fl = DeviceTrnData(mat, 'cuda', seed=77, epoch_period=2)
+    fl_loader = DeviceLoader(fl, 256, seed=6)
+    sums = []
+    for epoch in range(4):
+        fl.sample_negs()
+        batches = list(fl_loader)
+        assert all(len(b) == 4 for b in batches)
+        flags, pairs = torch.cat([b[3] for b in batches]), torch.cat([torch.stack(b[:2], 1) for b in batches])
+        sums.append(int(flags.sum()))
+        if epoch == 1:
+            assert pairs[flags.bool()].cpu().tolist() == [[int(mat.row[0]), int(mat.col[0])]]
+    assert sums == [1, 1, 0, 1]
+    # two data-parallel ranks split the same permutation without overlap
+    parts = [torch.cat([torch.stack(b[:2], 1) for b in DeviceLoader(ds, 256, rank=r, world=2, seed=9)]) for r in range(2)]
+    both = torch.cat(parts).cpu().numpy()
+    assert len(np.unique(both[:, 0] * n_item + both[:, 1])) == len(rows) and abs(len(parts[0]) - len(parts[1])) == 0
+
+
+@pytest.mark.parametrize('n,dim,K', [(5000, 64, 50), (700, 32, 7), (3000, 128, 50), (40, 16, 3)])
+def test_kmeans_matches_oracle_and_is_deterministic(n, dim, K):
+    from sslrec_b200.kmeans import KMeansClustering
+    g = torch.Generator().manual_seed(23)
+    centers = torch.randn(K, dim, generator=g)
+    x = centers[torch.randint(0, K, (n,), generator=g)] * 0.5 + 0.1 * torch.randn(n, dim, generator=g)
+    init = torch.rand(K, dim, generator=g)
+    km = KMeansClustering(K, dim, iters=64, check_every=4)
+    km.init_centroids = init
+    cents, idx, cnt = km(x.cuda())
+    ref_c, ref_i, ref_n = O.kmeans(x.double(), init.double(), iters=km.last_iters)
+    agree = (idx.cpu() == ref_i).double().mean().item()
+    assert agree >= 0.999, agree                       # fp32 vs fp64 distances may flip a near-tie
+    if agree == 1.0:
+        H.close(cents, ref_c, 1e-5, 1e-6, 'centroids')
+        assert torch.equal(cnt.cpu().double(), ref_n)
+    assert int(cnt.sum().item()) == n and cnt.shape == (K, 1) and idx.dtype == torch.int64
+    c2, i2, n2 = km(x.cuda())
+    assert torch.equal(c2, cents) and torch.equal(i2, idx) and torch.equal(n2, cnt)     # no floating-point atomics
+    # a single iteration against the formula: assignment to the nearest initial centroid, mean of the members
+    km1 = KMeansClustering(K, dim, iters=1)
+    km1.init_centroids = init
+    c1, i1, n1 = km1(x.cuda())
+    d2 = (x.double().unsqueeze(1) - init.double().unsqueeze(0)).square().sum(-1)
+    near = d2.argmin(1)
+    margin = d2.topk(2, dim=1, largest=False).values
+    safe = (margin[:, 1] - margin[:, 0]) > 1e-4 * margin[:, 1] if K > 1 else torch.ones(n, dtype=torch.bool)
+    assert torch.equal(i1.cpu()[safe], near[safe])

@@ -105,3 +105,29 @@ def test_negative_sampler_never_returns_a_positive():
     pos = set(zip(case['rows'].tolist(), case['cols'].tolist()))
     assert all((u, j) not in pos for u, j in zip(case['rows'].tolist(), negs.tolist()))
     assert negs.min() >= 0 and negs.max() < case['n_item']
+
+
+def test_philox_known_answers_and_sampler_properties():
+    """Random123's published Philox4x32-10 known-answer vectors pin the numpy generator that the GPU tests compare
+    the in-kernel draws with; the rejection sampler on top of it never returns a training positive."""
+    from oracle import philox as P
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff, 0xffffffff), (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0), (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, want in kat:
+        got = P.philox4x32_10(*[np.array([c]) for c in ctr], key[0] | (key[1] << 32))
+        assert tuple(int(g[0]) for g in got) == want
+    import scipy.sparse as sp
+    rows, cols = inputs.bipartite_edges(40, 9, 250, 3)
+    csr = sp.csr_matrix((np.ones(len(rows)), (rows, cols)), shape=(40, 9))
+    csr.sort_indices()
+    coo = csr.tocoo()
+    negs = P.sample_negs(coo.row, csr.indptr, csr.indices, 9, seed=5, epoch=0)
+    pos = set(zip(coo.row.tolist(), coo.col.tolist()))
+    full = set(np.flatnonzero(np.diff(csr.indptr) == 9).tolist())           # users who interacted with everything
+    assert all((int(u), int(j)) not in pos for u, j in zip(coo.row, negs) if int(u) not in full)
+    assert negs.min() >= 0 and negs.max() < 9
+    assert not np.array_equal(negs, P.sample_negs(coo.row, csr.indptr, csr.indices, 9, seed=5, epoch=1))
+    u = P.noise_uniform(11, 1, 64, 10)
+    assert u.shape == (64, 10) and u.dtype == np.float32 and 0.0 <= u.min() and u.max() < 1.0
+    assert abs(P.edge_keep(3, 0, np.arange(20000) % 500, np.arange(20000) // 500, 0.25).mean() - 0.25) < 0.02
