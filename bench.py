@@ -41,6 +41,7 @@ WORKLOADS = {
     'lightgcn-xl-8th': ('lightgcn', 'synthetic-xl-8th', dict(layer_num=3, embedding_size=128, reg_weight=1.0e-8, keep_rate=1.0)),
     'ncl-amazon': ('ncl', 'amazon', dict(layer_num=3, embedding_size=64, high_order=2, reg_weight=1.0e-7, proto_weight=1.0e-4,
                                          struct_weight=1.0e-3, temperature=0.1, epoch_period=3, cluster_num=50, keep_rate=1.0)),
+    'directau-gowalla': ('directau', 'gowalla', dict(layer_num=2, embedding_size=64, gamma=2.0)),
     'hccf-amazon': ('hccf', 'amazon', dict(layer_num=2, embedding_size=64, reg_weight=1.0e-7, cl_weight=1.0, temperature=0.1,
                                            keep_rate=0.5, mult=1.0, hyper_num=128, leaky=0.5)),
 }
@@ -188,6 +189,9 @@ def run_reference(args):
     if rank != 0:
         return
     model, graph, hp = WORKLOADS[args.workload]
+    if model not in ('lightgcn', 'simgcl', 'sgl', 'directau'):
+        print(json.dumps({'impl': 'reference', 'unavailable': f'oracle.CpuTrainer has no whole-step driver for {model} (per-call oracle only)'}))
+        return
     rows, cols, n_user, n_item = graph_arrays(graph)
     batches = make_batches(rows, cols, n_item, max(2, min(args.steps + args.warmup, 8)))
     times, threads = cpu_steps(model, hp, rows, cols, n_user, n_item, batches, budget_s=170.0, max_steps=args.steps,
@@ -502,7 +506,7 @@ def run_ours(args):
 
     # ---- CPU baseline on this box's host cores (bounded sample) ----
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and model_name in ('lightgcn', 'simgcl', 'sgl', 'directau'):      # models oracle.CpuTrainer steps
         times, threads = cpu_steps(model_name, hp, rows, cols, n_user, n_item, [b.numpy() for b in host_batches[:3]],
                                    budget_s=45.0, max_steps=2, warmup=1)
         cpu = {'value': 1.0 / float(np.median(times)), 'unit': 'steps/s', 'cores': threads, 'kind': 'port',

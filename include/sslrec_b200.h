@@ -159,7 +159,8 @@ SSL_API int ssl_bpr_bwd(const float *users, int64_t u_stride, const float *items
  * (loss_utils.py:30-39 cal_infonce_loss; :42-51 cal_infonce_loss_spec_nodes with norm_mode 1).
  *
  * ssl_rows_normalize  x^ = x / sqrt(1e-8 + |x|^2)  (norm_mode 0, loss_utils.py:33-35) or
- *                     F.normalize(x + 1e-8)        (norm_mode 1, loss_utils.py:45-46);
+ *                     F.normalize(x + 1e-8)        (norm_mode 1, loss_utils.py:45-46) or
+ *                     F.normalize(x)               (norm_mode 2, loss_utils.py:78,85);
  *   optional gather (idx != NULL: row i of the output is x[idx[i]]), optional scale of the
  *   output (alpha), writes row-major out [n, dim], the K-major tile copy out_t
  *   [ceil(n/64), dim, 64] the streaming side of ssl_softmax_gemm reads (may be NULL),
@@ -239,6 +240,23 @@ SSL_API int ssl_predict_mask(const float *users_tab, int64_t u_stride, const flo
                      const int64_t *users, int64_t n_b, int64_t n_item, int32_t dim, const int64_t *mask_dense,
                      const int32_t *trn_rowptr, const int32_t *trn_cols, float *preds, void *stream);
 SSL_API int ssl_topk(const float *preds, int64_t n_b, int64_t n_item, int32_t k, int64_t *out_idx, float *out_val, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * SURVEY 8(f) row 4  DirectAU's losses (loss_utils.py:75-86) on unit rows x^ = F.normalize(x)
+ * (ssl_rows_normalize with norm_mode 2).
+ * ssl_align_fwd: loss_b[b] = |x^_b - y^_b|^2 (alignment, alpha = 2; the caller averages).
+ * uniformity(x) = log mean_{i<j} exp(-2 |x^_i - x^_j|^2): the pair sum is ssl_softmax_gemm[_tf32x3]
+ *   with R = 4 log2(e) x^, C = x^, offset = 4 log2(e); ssl_uniform_finalize reduces its split partials
+ *   and removes the i == j term: pair_sum[i] = sum_{j!=i} e_ij, w[i,:] = sum_{j!=i} e_ij x^_j.
+ * ssl_unit_rows_bwd: dx^_b = scale * (*gscale) * (c1 d1_b + c2 d2_b) pushed through the normalisation,
+ *   g_out[idx[b]] += rinv_b (dx^_b - x^_b (x^_b . dx^_b))   (d2 may be NULL; idx NULL = identity).
+ * ------------------------------------------------------------------------------------------ */
+SSL_API int ssl_align_fwd(const float *xhat, const float *yhat, int64_t batch, int32_t dim, float *loss_b, void *stream);
+SSL_API int ssl_uniform_finalize(const float *rowsum_part, const float *o_part, int32_t n_split, int64_t batch, int32_t dim,
+                         const float *r_scaled, const float *xhat, float offset, float *pair_sum, float *w, void *stream);
+SSL_API int ssl_unit_rows_bwd(const float *xhat, const float *rinv, const int64_t *idx, int64_t batch, int32_t dim, const float *d1,
+                      float c1, const float *d2, float c2, const float *gscale, float scale, float *g_out, int64_t g_stride,
+                      void *stream);
 
 /* ------------------------------------------------------------------------------------------
  * a17  KMeansClustering (aug_utils.py:142-157, NCL): one Lloyd iteration = assignment

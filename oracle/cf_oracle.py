@@ -287,6 +287,29 @@ def lightgcn_loss(adj: Adj, user_e, item_e, batch, layer_num: int, reg_weight: f
     return bpr + reg, {'bpr_loss': bpr, 'reg_loss': reg}
 
 
+def alignment(x: torch.Tensor, y: torch.Tensor, alpha: int = 2) -> torch.Tensor:
+    """loss_utils.py:75-79."""
+    x, y = F.normalize(x, dim=-1), F.normalize(y, dim=-1)
+    return (x - y).norm(p=2, dim=1).pow(alpha).mean()
+
+
+def uniformity(x: torch.Tensor) -> torch.Tensor:
+    """loss_utils.py:82-86: log of the mean over the B(B-1)/2 row pairs of exp(-2 ||x^_i - x^_j||^2)."""
+    x = F.normalize(x, dim=-1)
+    return torch.pdist(x, p=2).pow(2).mul(-2).exp().mean().log()
+
+
+def directau_loss(adj: Adj, user_e, item_e, batch, layer_num: int, gamma: float):
+    """DirectAU.cal_loss (models/general_cf/directau.py:38-48); embeddings are the layer MEAN (:33)."""
+    ancs, poss = batch[0], batch[1]
+    e = lightgcn_embeds(adj.torch_coo(user_e.dtype), torch.cat([user_e, item_e], 0), layer_num) / (layer_num + 1)
+    ue, ie = _split(e, adj.n_user)
+    a, p = ue[ancs], ie[poss]
+    align = alignment(a, p)
+    uniform = gamma * (uniformity(a) + uniformity(p)) / 2
+    return align + uniform, {'align_loss': align, 'uniform_loss': uniform}
+
+
 def simgcl_loss(adj: Adj, user_e, item_e, batch, layer_num: int, reg_weight: float, cl_weight: float,
                 temperature: float, eps: float, uniforms1, uniforms2):
     """SimGCL.cal_loss (models/general_cf/simgcl.py:39-55): two perturbed views + one clean view."""
@@ -484,6 +507,8 @@ class CpuTrainer:
             eks = [keep_mask_from_uniform(torch.rand(adj.nnz, generator=self.gen), keep).numpy() for _ in range(2)]
             loss, _ = sgl_loss(adj, self.user_e, self.item_e, batch, hp['layer_num'], hp['reg_weight'], hp['cl_weight'],
                                hp['temperature'], 'edge_drop', keep, edge_keeps=eks)
+        elif self.model == 'directau':
+            loss, _ = directau_loss(adj, self.user_e, self.item_e, batch, hp['layer_num'], hp['gamma'])
         else:
             raise ValueError(self.model)
         val = loss.item()

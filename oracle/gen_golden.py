@@ -41,9 +41,11 @@ MODEL_HP = {
     'sgl_nd': dict(layer_num=2, keep_rate=0.5, augmentation='node_drop'),
     'ncl': dict(layer_num=3, high_order=2, cluster_num=5),
     'hccf': dict(layer_num=2, keep_rate=0.5, hyper_num=16, leaky=0.5),
+    'directau': dict(layer_num=2, gamma=2.0),
 }
 CASES = [('lightgcn', 'tiny'), ('simgcl', 'tiny'), ('sgl', 'tiny'), ('sgl_nd', 'tiny'), ('ncl', 'tiny'),
-         ('hccf', 'tiny'), ('lightgcn', 'small'), ('simgcl', 'small'), ('sgl', 'small'), ('simgcl', 'mid')]
+         ('hccf', 'tiny'), ('lightgcn', 'small'), ('simgcl', 'small'), ('sgl', 'small'), ('simgcl', 'mid'),
+         ('directau', 'tiny'), ('directau', 'small')]
 
 
 def _scratch(case):
@@ -210,6 +212,8 @@ def run_one(model_key: str, case_name: str):
         out.pop('adj_rows'); out.pop('adj_cols')
         out['adj_vals_sum'] = np.float64(out.pop('adj_vals').astype(np.float64).sum())
     out['hp_json'] = np.array(repr({k: mc[k] for k in sorted(mc) if k != 'name'}))
+    out['opt_lr'] = np.float64(configs['optimizer']['lr'])                     # trainer.py:45-49
+    out['opt_weight_decay'] = np.float64(configs['optimizer']['weight_decay'])
     os.makedirs(OUT, exist_ok=True)
     path = os.path.join(OUT, f'{model_key}_{case_name}.npz')
     np.savez_compressed(path, **out)

@@ -102,6 +102,8 @@ def oracle_loss(model_key: str, case: Dict, hp: Dict, adj: O.Adj, dr: Dict, para
             ic, i2c, _ = O.kmeans(ie.detach(), dr['init_item_centroids'].to(dt))
         return O.ncl_loss(adj, ue, ie, batch, hp['layer_num'], hp['high_order'], hp['reg_weight'], hp['proto_weight'],
                           hp['struct_weight'], hp['temperature'], uc, u2c, ic, i2c)
+    if model == 'directau':
+        return O.directau_loss(adj, ue, ie, batch, hp['layer_num'], hp['gamma'])
     if model == 'hccf':
         return O.hccf_loss(adj, ue, ie, params['user_hyper_embeds'], params['item_hyper_embeds'], batch,
                            hp['layer_num'], hp['reg_weight'], hp['cl_weight'], hp['temperature'], hp['keep_rate'],
@@ -120,7 +122,8 @@ def clean_embeds(model_key: str, adj: O.Adj, hp: Dict, params: Dict):
         e, _, _ = O.hccf_embeds(adj, ue, ie, params['user_hyper_embeds'], params['item_hyper_embeds'], hp['layer_num'],
                                 1.0, hp['mult'], hp['leaky'])
         return e
-    return O.lightgcn_embeds(a_t, e0, hp['layer_num'])
+    e = O.lightgcn_embeds(a_t, e0, hp['layer_num'])
+    return e / (hp['layer_num'] + 1) if model == 'directau' else e      # directau.py:33: mean over the layers
 
 
 def oracle_outputs(model_key: str, case_name: str, dtype=torch.float32, golden: Dict = None) -> Dict:
@@ -155,6 +158,7 @@ def oracle_outputs(model_key: str, case_name: str, dtype=torch.float32, golden: 
         top = torch.topk(preds, k=min(40, I))
         out['topk_idx'], out['topk_val'] = top.indices, top.values
         for k, p in params.items():
-            newp, _, _ = O.adam_update(p.detach(), p.grad, torch.zeros_like(p), torch.zeros_like(p), 1, 1e-3)
+            newp, _, _ = O.adam_update(p.detach(), p.grad, torch.zeros_like(p), torch.zeros_like(p), 1, float(golden.get('opt_lr', 1e-3)),
+                                       weight_decay=float(golden.get('opt_weight_decay', 0.0)))
             out['new_' + k] = newp
     return out

@@ -73,6 +73,9 @@ def _load():
         'ssl_adam_step': (C.c_int, [vp, vp, vp, vp, i64, i64, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, vp]),
         'ssl_predict_mask': (C.c_int, [vp, i64, vp, i64, vp, i64, i64, i32, vp, vp, vp, vp, vp]),
         'ssl_topk': (C.c_int, [vp, i64, i64, i32, vp, vp, vp]),
+        'ssl_align_fwd': (C.c_int, [vp, vp, i64, i32, vp, vp]),
+        'ssl_uniform_finalize': (C.c_int, [vp, vp, i32, i64, i32, vp, vp, f32, vp, vp, vp]),
+        'ssl_unit_rows_bwd': (C.c_int, [vp, vp, vp, i64, i32, vp, f32, vp, f32, vp, f32, vp, i64, vp]),
         'ssl_kmeans_workspace': (C.c_int, [i64, i32, i32, c_i32p, c_i32p]),
         'ssl_kmeans_iter': (C.c_int, [vp, i64, i64, i32, i32, vp, vp, vp, vp, vp, vp, vp]),
         'ssl_sample_negs': (C.c_int, [vp, i64, vp, vp, i64, C.c_uint64, C.c_uint32, vp, vp]),

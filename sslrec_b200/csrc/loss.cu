@@ -409,7 +409,7 @@ extern "C" int ssl_rows_normalize(const float *x, int64_t stride, const int64_t 
     SSL_CHECK_ARG((out_hi == nullptr) == (out_lo == nullptr) && (out_thi == nullptr) == (out_tlo == nullptr), "ssl_rows_normalize: hi and lo outputs go together");
     SSL_CHECK_ARG(out_thi == nullptr || (t_pitch >= (n + 63) / 64 * 64 && t_pitch % 4 == 0), "ssl_rows_normalize: t_pitch must be >= ceil64(n) and a multiple of 4");
     SSL_CHECK_ARG(dim >= 4 && dim <= SSL_MAX_DIM && dim % 4 == 0, "ssl_rows_normalize: dim %d must be a multiple of 4 <= %d", dim, SSL_MAX_DIM);
-    SSL_CHECK_ARG(norm_mode == 0 || norm_mode == 1, "ssl_rows_normalize: bad norm_mode");
+    SSL_CHECK_ARG(norm_mode >= 0 && norm_mode <= 2, "ssl_rows_normalize: bad norm_mode");
     if (n == 0) return SSL_OK;
     const size_t smem = sizeof(float) * 64 * (dim + 1);
     rows_normalize_kernel<<<(unsigned)((n + 63) / 64), 256, smem, STREAM>>>(x, stride, idx, n, dim, norm_mode, alpha, out, out_t, rinv, out_hi, out_lo, out_thi, out_tlo, t_pitch);

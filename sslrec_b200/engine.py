@@ -714,6 +714,164 @@ def infonce_loss_sum(e1: Rows, e2: Rows, table: Rows, idx, temp: float, idx2=Non
     return _InfoNceFn.apply(e1, e2, table, idx, idx2, float(temp), 0, False, 0.0, *_tokens(e1, e2, table))
 
 
+# ---- DirectAU: alignment / uniformity on unit rows (loss_utils.py:75-86) -----------------------------------
+
+def _unit_rows(e: Rows, idx, alpha: float, streamed: bool, use_tc: bool):
+    """F.normalize of the gathered rows e[idx] (norm_mode 2), scaled by ``alpha``; with the operand copies the
+    contraction reads when asked (``streamed``: the C side needs the transposed copies as well)."""
+    dev, d, B = e.base.device, e.dim, idx.numel()
+    Bp = ceil_to(B, 64)
+    f = dict(device=dev, dtype=torch.float32)
+    out, rinv = torch.empty(Bp, d, **f), torch.empty(B, **f)
+    hi = lo = thi = tlo = out_t = None
+    if use_tc:
+        hi, lo = torch.empty(Bp, d, **f), torch.empty(Bp, d, **f)
+        if streamed:
+            thi, tlo = torch.empty(d, Bp, **f), torch.empty(d, Bp, **f)
+    elif streamed:
+        out_t = torch.empty(Bp // 64, d, 64, **f)
+    with torch.cuda.device(dev):
+        check(lib.ssl_rows_normalize(e.ptr, e.stride, idx.data_ptr(), B, d, 2, alpha, out.data_ptr(), _ptr(out_t), rinv.data_ptr(),
+                                     _ptr(hi), _ptr(lo), _ptr(thi), _ptr(tlo), Bp, _stream(e.base)), 'ssl_rows_normalize(unit)')
+    return out, rinv, (hi, lo, thi, tlo, out_t)
+
+
+def _align_fwd(x: Rows, y: Rows, ix, iy):
+    """alignment(x, y, alpha=2) = mean_b |x^_b - y^_b|^2 (loss_utils.py:75-79)."""
+    dev, d, B = x.base.device, x.dim, ix.numel()
+    xh, rx, _ = _unit_rows(x, ix, 1.0, False, False)
+    yh, ry, _ = _unit_rows(y, iy, 1.0, False, False)
+    loss_b, out = torch.empty(B, device=dev), torch.empty((), device=dev)
+    with torch.cuda.device(dev):
+        s = _stream(x.base)
+        check(lib.ssl_align_fwd(xh.data_ptr(), yh.data_ptr(), B, d, loss_b.data_ptr(), s), 'ssl_align_fwd')
+        check(lib.ssl_sum(loss_b.data_ptr(), B, 1.0 / B, out.data_ptr(), s), 'ssl_sum')
+    return out, (x, y, ix, iy, xh, yh, rx, ry)
+
+
+def _align_bwd(pack, g):
+    x, y, ix, iy, xh, yh, rx, ry = pack
+    B, d = ix.numel(), x.dim
+    g = g.contiguous()
+    c = 2.0 / B                                                # d/dx^ mean |x^ - y^|^2 = 2 (x^ - y^) / B
+    with torch.cuda.device(g.device):
+        s = _stream(g)
+        for (rows, idx, a, b, ri) in ((x, ix, xh, yh, rx), (y, iy, yh, xh, ry)):
+            gp = rows.grad_ptr()
+            if gp is not None:
+                check(lib.ssl_unit_rows_bwd(a.data_ptr(), ri.data_ptr(), idx.data_ptr(), B, d, a.data_ptr(), c, b.data_ptr(), -c,
+                                            g.data_ptr(), 1.0, gp, rows.stride, s), 'ssl_unit_rows_bwd(align)')
+
+
+def _uniform_fwd(x: Rows, ix):
+    """uniformity(x) = log mean_{i<j} exp(-2 |x^_i - x^_j|^2) (loss_utils.py:82-86): the B x B pair sum runs on the
+    InfoNCE contraction kernel (R = 4 log2e x^, C = x^), never materialising pdist's B(B-1)/2 vector."""
+    dev, d, B = x.base.device, x.dim, ix.numel()
+    if B < 2:
+        raise ValueError('uniformity needs at least 2 rows')
+    Bp = ceil_to(B, 64)
+    use_tc = USE_TENSOR_CORES and d in (32, 64)
+    off = 4.0 * LOG2E
+    r, _, (r_hi, r_lo, _, _, _) = _unit_rows(x, ix, off, False, use_tc)
+    c, rinv, (c_hi, c_lo, c_thi, c_tlo, c_t) = _unit_rows(x, ix, 1.0, True, use_tc)
+    f = dict(device=dev, dtype=torch.float32)
+    n_split = choose_split((B + 127) // 128, Bp // 64, slots=148 if use_tc else 296, prefer_few=use_tc)
+    rs_part, o_part = torch.zeros(n_split, B, **f), torch.zeros(n_split, B, d, **f)
+    pair_sum, w, total = torch.empty(B, **f), torch.empty(B, d, **f), torch.empty((), **f)
+    with torch.cuda.device(dev):
+        s = _stream(x.base)
+        with _timed('nce_gemm_fwd', dict(B=B, n=B, dim=d, tc=use_tc)):
+            if use_tc:
+                check(lib.ssl_softmax_gemm_tf32x3(r_hi.data_ptr(), r_lo.data_ptr(), B, c_hi.data_ptr(), c_lo.data_ptr(), c_thi.data_ptr(),
+                                                  c_tlo.data_ptr(), Bp, B, d, None, off, n_split, rs_part.data_ptr(), o_part.data_ptr(), s),
+                      'ssl_softmax_gemm_tf32x3(uniformity)')
+            else:
+                check(lib.ssl_softmax_gemm(r.data_ptr(), B, c.data_ptr(), c_t.data_ptr(), B, d, None, off, n_split,
+                                           rs_part.data_ptr(), o_part.data_ptr(), s), 'ssl_softmax_gemm(uniformity)')
+        check(lib.ssl_uniform_finalize(rs_part.data_ptr(), o_part.data_ptr(), n_split, B, d, r.data_ptr(), c.data_ptr(), off,
+                                       pair_sum.data_ptr(), w.data_ptr(), s), 'ssl_uniform_finalize')
+        check(lib.ssl_sum(pair_sum.data_ptr(), B, 1.0, total.data_ptr(), s), 'ssl_sum')
+    out = torch.log(total / float(B * (B - 1)))                 # total counts every unordered pair twice
+    return out, (x, ix, c, rinv, w, total)
+
+
+def _uniform_bwd(pack, g):
+    x, ix, c, rinv, w, total = pack
+    gp = x.grad_ptr()
+    if gp is None:
+        return
+    coef = (g * 8.0 / total).contiguous()                       # d total / d x^_i = 8 sum_{j != i} e_ij x^_j
+    with torch.cuda.device(g.device):
+        check(lib.ssl_unit_rows_bwd(c.data_ptr(), rinv.data_ptr(), ix.data_ptr(), ix.numel(), x.dim, w.data_ptr(), 1.0, None, 0.0,
+                                    coef.data_ptr(), 1.0, gp, x.stride, _stream(g)), 'ssl_unit_rows_bwd(uniformity)')
+
+
+class _AlignFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x: Rows, y: Rows, ix, iy, *tokens):
+        out, ctx.pack = _align_fwd(x, y, ix, iy)
+        ctx.nt = len(tokens)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        _align_bwd(ctx.pack, g)
+        return (None,) * 4 + (torch.zeros((), device=g.device),) * ctx.nt
+
+
+class _UniformFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x: Rows, ix, *tokens):
+        out, ctx.pack = _uniform_fwd(x, ix)
+        ctx.nt = len(tokens)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        _uniform_bwd(ctx.pack, g)
+        return (None,) * 2 + (torch.zeros((), device=g.device),) * ctx.nt
+
+
+def alignment_mean(x: Rows, y: Rows, ix, iy) -> torch.Tensor:
+    dev = x.base.device
+    return _AlignFn.apply(x, y, _i64(ix, dev), _i64(iy, dev), *_tokens(x, y))
+
+
+def uniformity_log_mean(x: Rows, ix) -> torch.Tensor:
+    return _UniformFn.apply(x, _i64(ix, x.base.device), *_tokens(x))
+
+
+class _DenseAlignFn(torch.autograd.Function):
+    """alignment on plain dense [B, d] tensors (the reference's signature)."""
+
+    @staticmethod
+    def forward(ctx, x, y):
+        ar = torch.arange(x.shape[0], device=x.device)
+        rx, sx = _dense_rows(x, True)
+        ry, sy = _dense_rows(y, True)
+        out, ctx.pack = _align_fwd(rx, ry, ar, ar)
+        ctx.sinks = (sx, sy)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        _align_bwd(ctx.pack, g)
+        return ctx.sinks[0](), ctx.sinks[1]()
+
+
+class _DenseUniformFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        rx, ctx.sink = _dense_rows(x, True)
+        out, ctx.pack = _uniform_fwd(rx, torch.arange(x.shape[0], device=x.device))
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        _uniform_bwd(ctx.pack, g)
+        return ctx.sink()
+
+
 # ---- the same kernels behind plain dense tensors (reference signatures; gradients are returned
 # ---- as ordinary dense tensors -- used by HCCF, whose hyper-graph branch lives in torch autograd)
 

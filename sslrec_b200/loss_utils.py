@@ -30,6 +30,24 @@ def cal_infonce_loss_spec_nodes(embeds1, embeds2, nodes, temp):
     return E.dense_infonce_spec_nodes_mean(embeds1, embeds2, nodes, temp)
 
 
+def alignment(x, y, alpha=2, *idx):
+    """loss_utils.py:75-79 (alpha = 2 only).  Dense: (x [B,d], y [B,d]).  Fused: (users Rows, items Rows, ancs, poss)
+    -- ``alpha`` then holds ``ancs``."""
+    if isinstance(x, E.Rows):
+        ancs, poss = (alpha,) + idx
+        return E.alignment_mean(x, y, ancs, poss)
+    if alpha != 2:
+        raise NotImplementedError('alignment: only alpha = 2 (the value every caller in the reference uses)')
+    return E._DenseAlignFn.apply(x, y)
+
+
+def uniformity(x, idx=None):
+    """loss_utils.py:82-86.  Dense: (x [B,d]).  Fused: (Rows, idx)."""
+    if isinstance(x, E.Rows):
+        return E.uniformity_log_mean(x, idx)
+    return E._DenseUniformFn.apply(x)
+
+
 def reg_params(model_or_state):
     """loss_utils.py:20-24: sum_W ||W||_2^2 over all parameters.  With a PropState the embedding
     table's part comes from the deterministic reduction kernel and its gradient is fused into the

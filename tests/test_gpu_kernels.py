@@ -374,3 +374,30 @@ def test_kmeans_matches_oracle_and_is_deterministic(n, dim, K):
     margin = d2.topk(2, dim=1, largest=False).values
     safe = (margin[:, 1] - margin[:, 0]) > 1e-4 * margin[:, 1] if K > 1 else torch.ones(n, dtype=torch.bool)
     assert torch.equal(i1.cpu()[safe], near[safe])
+
+
+@pytest.mark.parametrize('use_tc', [True, False])
+@pytest.mark.parametrize('dim,B', [(64, 4096), (32, 100), (128, 300), (48, 257), (64, 2)])
+def test_alignment_uniformity_forward_backward(dim, B, use_tc, monkeypatch):
+    """DirectAU's losses (loss_utils.py:75-86) with the reference's dense signatures against the float64 oracle;
+    the uniformity pair sum runs on the InfoNCE contraction (tcgen05 3xTF32 at dims 32 / 64, FP32 FMA otherwise)."""
+    from sslrec_b200 import engine
+    from sslrec_b200 import loss_utils as LU
+    monkeypatch.setattr(engine, 'USE_TENSOR_CORES', use_tc)
+    g = torch.Generator().manual_seed(31)
+    x = torch.randn(B, dim, generator=g) * 0.3
+    y = x * 0.5 + torch.randn(B, dim, generator=g) * 0.2
+    if B > 10:
+        x[7] = x[3]                                           # duplicated rows (the same user twice in a batch): pair distance 0
+    xs = [t.clone().cuda().requires_grad_(True) for t in (x, y)]
+    loss = LU.alignment(xs[0], xs[1]) + 2.0 * (LU.uniformity(xs[0]) + LU.uniformity(xs[1])) / 2
+    loss.backward()
+    ref = [t.double().clone().requires_grad_(True) for t in (x, y)]
+    want = O.alignment(ref[0], ref[1]) + 2.0 * (O.uniformity(ref[0]) + O.uniformity(ref[1])) / 2
+    want.backward()
+    assert abs(loss.item() - want.item()) <= 1e-5 * max(1.0, abs(want.item())), (loss.item(), want.item())
+    for a, b, name in zip(xs, ref, 'xy'):
+        H.close(a.grad, b.grad, 2e-4, 2e-5 * b.grad.abs().max().item(), 'grad_' + name)
+    # the single terms, and the fp32 reference formula (pdist) for the record
+    assert abs(LU.uniformity(xs[0].detach()).item() - O.uniformity(x.double()).item()) <= 1e-5
+    assert abs(LU.alignment(xs[0].detach(), xs[1].detach()).item() - O.alignment(x.double(), y.double()).item()) <= 1e-5

@@ -13,7 +13,8 @@ import ssl_test_helpers as H
 pytestmark = pytest.mark.gpu
 
 CASES = [('lightgcn', 'tiny'), ('simgcl', 'tiny'), ('sgl', 'tiny'), ('sgl_nd', 'tiny'), ('ncl', 'tiny'), ('hccf', 'tiny'),
-         ('lightgcn', 'small'), ('simgcl', 'small'), ('sgl', 'small'), ('simgcl', 'mid')]
+         ('lightgcn', 'small'), ('simgcl', 'small'), ('sgl', 'small'), ('simgcl', 'mid'),
+         ('directau', 'tiny'), ('directau', 'small')]
 
 
 def _run(model_key, case_name):
@@ -42,7 +43,8 @@ def _run(model_key, case_name):
 def test_cal_loss_backward_adam_match_reference(model_key, case_name):
     from sslrec_b200.optim import FusedAdam
     g, case, model, batch = _run(model_key, case_name)
-    opt = FusedAdam(model.parameters(), lr=1e-3, weight_decay=0)
+    wd = float(g.get('opt_weight_decay', 0.0))            # directau.yml: 1e-6; the other YAMLs: 0
+    opt = FusedAdam(model.parameters(), lr=float(g.get('opt_lr', 1e-3)), weight_decay=wd)
     opt.zero_grad()
     loss, parts = model.cal_loss(batch)
     assert abs(loss.item() - float(g['loss'])) <= 1e-5 * max(1.0, abs(float(g['loss']))), (loss.item(), float(g['loss']))
@@ -62,10 +64,16 @@ def test_cal_loss_backward_adam_match_reference(model_key, case_name):
             assert abs(gr.double().abs().sum().item() - g['grad_' + name + '_abssum']) <= 1e-4 * g['grad_' + name + '_abssum']
     opt.step()
     for name, p in model.named_parameters():
-        if 'new_' + name in g:
-            H.close(p, g['new_' + name], 1e-5, 2e-6, 'new_' + name)
-        else:
-            H.close(p[:32], g['new_' + name + '_head'], 1e-5, 2e-6, 'new_' + name)
+        full = 'new_' + name in g
+        ref = g['new_' + name] if full else g['new_' + name + '_head']
+        gref = g['grad_' + name] if full else g['grad_' + name + '_head']
+        got = (p if full else p[:32]).detach().cpu().numpy()
+        # entries whose reference gradient is rounding noise have no defined Adam sign (see test_oracle_golden.py)
+        case_p = case[{'user_embeds': 'user_e', 'item_embeds': 'item_e'}[name]].numpy() if name in ('user_embeds', 'item_embeds') else 0.0
+        gtot = gref + wd * (case_p if full or np.isscalar(case_p) else case_p[:32])       # Adam folds weight decay into g
+        noise = np.abs(gtot) <= 1e-5 * np.abs(gtot).max()
+        H.close(np.where(noise, ref, got), ref, 1e-5, 2e-6, 'new_' + name)
+        assert (np.abs(got - ref)[noise] <= 2.1e-3).all(), name
 
 
 @pytest.mark.parametrize('model_key,case_name', CASES)

@@ -10,7 +10,8 @@ from oracle import cf_oracle as O
 from oracle import inputs, replay
 
 CASES = [('lightgcn', 'tiny'), ('simgcl', 'tiny'), ('sgl', 'tiny'), ('sgl_nd', 'tiny'), ('ncl', 'tiny'),
-         ('hccf', 'tiny'), ('lightgcn', 'small'), ('simgcl', 'small'), ('sgl', 'small'), ('simgcl', 'mid')]
+         ('hccf', 'tiny'), ('lightgcn', 'small'), ('simgcl', 'small'), ('sgl', 'small'), ('simgcl', 'mid'),
+         ('directau', 'tiny'), ('directau', 'small')]
 
 
 def _close(a, b, rtol, atol, what):
@@ -61,10 +62,18 @@ def test_oracle_reproduces_reference(model_key, case_name):
             else:
                 _close(o[k], g[k], 1e-4, 1e-9, k)
         if k.startswith('new_'):
-            if k.endswith('_head'):
-                _close(o[k[:-5]][:32], g[k], 1e-6, 1e-7, k)
-            else:
-                _close(o[k], g[k], 1e-6, 1e-7, k)
+            got = o[k[:-5]][:32] if k.endswith('_head') else o[k]
+            gref = g['grad_' + k[4:]]
+            pname = k[4:-5] if k.endswith('_head') else k[4:]
+            if pname in ('user_embeds', 'item_embeds'):          # Adam folds weight decay (directau.yml: 1e-6) into g
+                p0 = o['case'][{'user_embeds': 'user_e', 'item_embeds': 'item_e'}[pname]].numpy()
+                gref = gref + float(g.get('opt_weight_decay', 0.0)) * (p0[:32] if k.endswith('_head') else p0)
+            # Adam's first step moves an entry by lr * g / (|g| + 1e-8): where the reference gradient is rounding noise
+            # (DirectAU has no regulariser, so rows far from the batch get ~1e-12 gradients) its sign, hence +-lr, is not
+            # defined; those entries only have to stay within 2 lr
+            noise = np.abs(gref) <= 1e-5 * np.abs(gref).max()
+            _close(np.where(noise, g[k], np.asarray(got)), g[k], 1e-6, 1e-7, k)
+            assert (np.abs(np.asarray(got) - g[k])[noise] <= 2.1e-3).all(), k
     if 'preds' in g:
         _close(o['preds'], g['preds'], 1e-5, 1e-6, 'preds')
     # top-K: identical indices wherever the reference's own score gap exceeds fp32 reassociation noise
