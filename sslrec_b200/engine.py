@@ -770,7 +770,9 @@ def _uniform_fwd(x: Rows, ix):
     if B < 2:
         raise ValueError('uniformity needs at least 2 rows')
     Bp = ceil_to(B, 64)
-    use_tc = USE_TENSOR_CORES and d in (32, 64)
+    # pair_sum_i = rowsum_i - e_ii cancels when the batch is tiny (e_ii = 1 against a handful of e_ij ~ 1e-2): there the
+    # FP32-FMA contraction (1e-7 relative) is used, the 3xTF32 one (1e-6) from 256 rows on, where the pair sum is >> e_ii
+    use_tc = USE_TENSOR_CORES and d in (32, 64) and B >= 256
     off = 4.0 * LOG2E
     r, _, (r_hi, r_lo, _, _, _) = _unit_rows(x, ix, off, False, use_tc)
     c, rinv, (c_hi, c_lo, c_thi, c_tlo, c_t) = _unit_rows(x, ix, 1.0, True, use_tc)
