@@ -86,3 +86,34 @@ def test_choose_split_fills_waves():
     assert choose_split(32, 1) == 1
     s = choose_split(655, 64)
     assert 1 <= s <= 16 and (655 * s) / (296 * -(-655 * s // 296)) > 0.95
+
+
+def test_device_side_components_fail_loudly_without_cuda():
+    """No host fallback: the device loader, the native k-means and the DirectAU losses refuse CPU inputs."""
+    from sslrec_b200 import loss_utils as LU
+    from sslrec_b200.data_handler import DeviceTrnData
+    from sslrec_b200.kmeans import KMeansClustering
+    trn = sp.coo_matrix((np.ones(3), ([0, 1, 2], [1, 0, 2])), shape=(3, 3))
+    with pytest.raises(RuntimeError, match='CUDA'):
+        DeviceTrnData(trn, 'cpu')
+    with pytest.raises(RuntimeError, match='CUDA'):
+        KMeansClustering(2, 4)(torch.zeros(8, 4))
+    with pytest.raises(RuntimeError, match='CUDA'):
+        LU.uniformity(torch.randn(8, 4))
+    with pytest.raises(RuntimeError, match='CUDA'):
+        LU.alignment(torch.randn(8, 4), torch.randn(8, 4))
+
+
+def test_batch_shard_coalesce_orders_by_parameter_position():
+    """Collectives must be issued in the same order on every rank although buffer addresses differ per process."""
+    from sslrec_b200.parallel import BatchShard
+    flat = torch.zeros(10, 2)
+    a, b, c = flat[:6], flat[6:], torch.zeros(5)
+    for order in ([c, a, b], [b, c, a], [a, b, c]):
+        bufs = BatchShard.coalesce(order)
+        pos_c = [i for i, t in enumerate(order) if t is c][0]
+        first = min(i for i, t in enumerate(order) if t is not c)
+        want = [20, 5] if first < pos_c else [5, 20]
+        assert [x.numel() for x in bufs] == want, [x.numel() for x in bufs]
+    nc = torch.zeros(4, 6)[:, :3]                                 # non-contiguous gradients travel alone
+    assert [x.numel() for x in BatchShard.coalesce([nc, a])] == [12, 12]
