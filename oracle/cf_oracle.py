@@ -393,6 +393,62 @@ def hccf_loss(adj: Adj, user_e, item_e, user_w, item_w, batch, layer_num: int, r
 
 
 # --------------------------------------------------------------------------------------
+# SURVEY 8(f) row 4  LightGCL (models/general_cf/lightgcl.py)
+# --------------------------------------------------------------------------------------
+
+def lightgcl_adjacency(trn_rows: np.ndarray, trn_cols: np.ndarray, n_user: int, n_item: int) -> Adj:
+    """The U x I matrix R / sqrt(rowD colD) of lightgcl.py:16-20 (float32 arithmetic throughout: the pickle is
+    cast to float32 at data_handler_general_cf.py:32) laid out as the symmetric bipartite Adj, so that one
+    propagation step [Z_u; Z_i] = A [E_u; E_i] is both ``_spmm(adj, E_i)`` and ``_spmm(adj^T, E_u)`` (:75-76)."""
+    pair = np.unique(np.asarray(trn_rows, dtype=np.int64) * n_item + np.asarray(trn_cols, dtype=np.int64))
+    ur, ic = pair // n_item, pair % n_item
+    row_d = np.bincount(ur, minlength=n_user).astype(np.float32)
+    col_d = np.bincount(ic, minlength=n_item).astype(np.float32)
+    v = (np.float32(1.0) / np.power(row_d[ur] * col_d[ic], np.float32(0.5))).astype(np.float32)
+    rows = np.concatenate([ur, ic + n_user])
+    cols = np.concatenate([ic + n_user, ur])
+    vals = np.concatenate([v, v])
+    order = np.lexsort((cols, rows))
+    return Adj(rows[order], cols[order], vals[order], n_user, n_item)
+
+
+def lightgcl_embeds(adj: Adj, user_e, item_e, layer_num: int, ut, vt, u_mul_s, v_mul_s, edge_keeps=None, dropout: float = 0.0):
+    """LightGCL.forward (lightgcl.py:70-95): E^(l) = A_drop E^(l-1) (no residual, :86-87), G_u^(l) = (U S)(V^T E_i^(l-1)),
+    G_i^(l) = (V S)(U^T E_u^(l-1)) (:79-83); returns the layer sums E_u, E_i, G_u, G_i (:90-93).
+    ``edge_keeps[l]``: keep mask of the directed entries at layer l+1 (the reference draws one F.dropout per direction,
+    :75-76), kept values are divided by 1 - dropout."""
+    nu = adj.n_user
+    dt = user_e.dtype
+    e_u, e_i = [user_e], [item_e]
+    g_u, g_i = [user_e], [item_e]
+    for layer in range(1, layer_num + 1):
+        keep = None if edge_keeps is None else edge_keeps[layer - 1]
+        a_t = edge_dropped(adj, keep, 1.0 - dropout, True, dt) if keep is not None else adj.torch_coo(dt)
+        z = torch.sparse.mm(a_t, torch.cat([e_u[-1], e_i[-1]], 0))
+        g_u.append(u_mul_s.to(dt) @ (vt.to(dt) @ e_i[-1]))
+        g_i.append(v_mul_s.to(dt) @ (ut.to(dt) @ e_u[-1]))
+        e_u.append(z[:nu])
+        e_i.append(z[nu:])
+    return sum(e_u), sum(e_i), sum(g_u), sum(g_i)
+
+
+def lightgcl_loss(adj: Adj, user_e, item_e, ws, batch, layer_num: int, reg_weight: float, cl_weight: float, temp: float,
+                  ut, vt, u_mul_s, v_mul_s, edge_keeps=None, dropout: float = 0.0):
+    """LightGCL.cal_loss (lightgcl.py:97-124).  ``ws``: the W_contrastive matrices, which only enter reg_params."""
+    ancs, poss, negs = batch
+    eu, ei, gu, gi = lightgcl_embeds(adj, user_e, item_e, layer_num, ut, vt, u_mul_s, v_mul_s, edge_keeps, dropout)
+    a, p, n = eu[ancs], ei[poss], ei[negs]
+    bpr = -((a * p).sum(-1) - (a * n).sum(-1)).sigmoid().log().mean()                                   # :104-106
+    neg_score = torch.log(torch.exp(gu[ancs] @ eu.T / temp).sum(1) + 1e-8).mean()                       # :112
+    neg_score = neg_score + torch.log(torch.exp(gi[poss] @ ei.T / temp).sum(1) + 1e-8).mean()           # :113
+    pos_score = (torch.clamp((gu[ancs] * eu[ancs]).sum(1) / temp, -5.0, 5.0)).mean() \
+        + (torch.clamp((gi[poss] * ei[poss]).sum(1) / temp, -5.0, 5.0)).mean()                          # :114-115
+    cl = (-pos_score + neg_score) * cl_weight
+    reg = reg_sumsq([user_e, item_e] + list(ws)) * reg_weight
+    return bpr + cl + reg, {'bpr_loss': bpr, 'reg_loss': reg, 'cl_loss': cl}
+
+
+# --------------------------------------------------------------------------------------
 # a17  k-means (models/aug_utils.py:142-157)
 # --------------------------------------------------------------------------------------
 

@@ -42,10 +42,11 @@ MODEL_HP = {
     'ncl': dict(layer_num=3, high_order=2, cluster_num=5),
     'hccf': dict(layer_num=2, keep_rate=0.5, hyper_num=16, leaky=0.5),
     'directau': dict(layer_num=2, gamma=2.0),
+    'lightgcl': dict(layer_num=2, dropout=0, cl_weight=0.1, reg_weight=1.0e-6, temp=0.1, svd_q=5),
 }
 CASES = [('lightgcn', 'tiny'), ('simgcl', 'tiny'), ('sgl', 'tiny'), ('sgl_nd', 'tiny'), ('ncl', 'tiny'),
          ('hccf', 'tiny'), ('lightgcn', 'small'), ('simgcl', 'small'), ('sgl', 'small'), ('simgcl', 'mid'),
-         ('directau', 'tiny'), ('directau', 'small')]
+         ('directau', 'tiny'), ('directau', 'small'), ('lightgcl', 'tiny'), ('lightgcl', 'small')]
 
 
 def _scratch(case):
@@ -130,6 +131,14 @@ def run_one(model_key: str, case_name: str):
         a = float(np.sqrt(6.0 / (D + H)))
         sd['user_hyper_embeds'] = (inputs.draw_uniform(gen, D, H) * 2 - 1) * a
         sd['item_hyper_embeds'] = (inputs.draw_uniform(gen, D, H) * 2 - 1) * a
+    if model_name == 'lightgcl':
+        a = float(np.sqrt(6.0 / (D + D)))
+        for li in range(mc['layer_num']):
+            sd[f'Ws.{li}.W'] = (inputs.draw_uniform(gen, D, D) * 2 - 1) * a       # W_contrastive: only reg_params sees it
+        out['svd_ut'], out['svd_vt'] = model.ut.numpy().copy(), model.vt.numpy().copy()       # t.svd_lowrank at lightgcl.py:25
+        out['svd_u_mul_s'], out['svd_v_mul_s'] = model.u_mul_s.numpy().copy(), model.v_mul_s.numpy().copy()
+        out['lgcl_rows'], out['lgcl_cols'] = model.adj.indices().numpy().copy()
+        out['lgcl_vals'] = model.adj.values().numpy().copy()
     model.load_state_dict(sd)
 
     L = mc['layer_num']

@@ -52,6 +52,9 @@ def draws(model_key: str, case: Dict, hp: Dict, adj: O.Adj) -> Dict:
         a = float(np.sqrt(6.0 / (D + H)))
         d['user_w'] = (inputs.draw_uniform(gen, D, H) * 2 - 1) * a
         d['item_w'] = (inputs.draw_uniform(gen, D, H) * 2 - 1) * a
+    if model == 'lightgcl':
+        a = float(np.sqrt(6.0 / (D + D)))
+        d['ws'] = [(inputs.draw_uniform(gen, D, D) * 2 - 1) * a for _ in range(L)]
     if model == 'lightgcn':
         d['edge_keep'] = edge_keep() if keep != 1.0 else None
     elif model == 'simgcl':
@@ -104,6 +107,11 @@ def oracle_loss(model_key: str, case: Dict, hp: Dict, adj: O.Adj, dr: Dict, para
                           hp['struct_weight'], hp['temperature'], uc, u2c, ic, i2c)
     if model == 'directau':
         return O.directau_loss(adj, ue, ie, batch, hp['layer_num'], hp['gamma'])
+    if model == 'lightgcl':
+        ladj = O.lightgcl_adjacency(case['rows'], case['cols'], case['n_user'], case['n_item'])
+        svd = [torch.from_numpy(golden['svd_' + k]) for k in ('ut', 'vt', 'u_mul_s', 'v_mul_s')]      # t.svd_lowrank draw of the reference run
+        ws = [params[f'Ws.{i}.W'] for i in range(hp['layer_num'])]
+        return O.lightgcl_loss(ladj, ue, ie, ws, batch, hp['layer_num'], hp['reg_weight'], hp['cl_weight'], hp['temp'], *svd)
     if model == 'hccf':
         return O.hccf_loss(adj, ue, ie, params['user_hyper_embeds'], params['item_hyper_embeds'], batch,
                            hp['layer_num'], hp['reg_weight'], hp['cl_weight'], hp['temperature'], hp['keep_rate'],
@@ -122,6 +130,11 @@ def clean_embeds(model_key: str, adj: O.Adj, hp: Dict, params: Dict):
         e, _, _ = O.hccf_embeds(adj, ue, ie, params['user_hyper_embeds'], params['item_hyper_embeds'], hp['layer_num'],
                                 1.0, hp['mult'], hp['leaky'])
         return e
+    if model == 'lightgcl':           # lightgcl.py:71-72,127: the cached E of the last training forward (dropout 0 here)
+        ladj = O.lightgcl_adjacency(adj.rows[adj.rows < adj.n_user], adj.cols[adj.rows < adj.n_user] - adj.n_user, adj.n_user, adj.n_item)
+        zu, zi = torch.zeros(1, adj.n_user, dtype=ue.dtype), torch.zeros(1, adj.n_item, dtype=ue.dtype)     # the SVD branch does not feed E
+        eu, ei, _, _ = O.lightgcl_embeds(ladj, ue, ie, hp['layer_num'], zu, zi, zu.T, zi.T)
+        return torch.cat([eu, ei], 0)
     e = O.lightgcn_embeds(a_t, e0, hp['layer_num'])
     return e / (hp['layer_num'] + 1) if model == 'directau' else e      # directau.py:33: mean over the layers
 
@@ -137,6 +150,8 @@ def oracle_outputs(model_key: str, case_name: str, dtype=torch.float32, golden: 
     if 'user_w' in dr:
         params['user_hyper_embeds'] = dr['user_w'].to(dtype).clone().requires_grad_(True)
         params['item_hyper_embeds'] = dr['item_w'].to(dtype).clone().requires_grad_(True)
+    for i, w in enumerate(dr.get('ws', [])):
+        params[f'Ws.{i}.W'] = w.to(dtype).clone().requires_grad_(True)
     out: Dict = {'adj': adj, 'draws': dr, 'case': case, 'hp': hp}
     loss, parts = oracle_loss(model_key, case, hp, adj, dr, params, golden)
     out['loss'] = loss.detach()

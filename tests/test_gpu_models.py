@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 
 CASES = [('lightgcn', 'tiny'), ('simgcl', 'tiny'), ('sgl', 'tiny'), ('sgl_nd', 'tiny'), ('ncl', 'tiny'), ('hccf', 'tiny'),
          ('lightgcn', 'small'), ('simgcl', 'small'), ('sgl', 'small'), ('simgcl', 'mid'),
-         ('directau', 'tiny'), ('directau', 'small')]
+         ('directau', 'tiny'), ('directau', 'small'), ('lightgcl', 'tiny'), ('lightgcl', 'small')]
 
 
 def _run(model_key, case_name):
@@ -66,7 +66,7 @@ def test_cal_loss_backward_adam_match_reference(model_key, case_name):
     for name, p in model.named_parameters():
         full = 'new_' + name in g
         ref = g['new_' + name] if full else g['new_' + name + '_head']
-        gref = g['grad_' + name] if full else g['grad_' + name + '_head']
+        gref = g['grad_' + name] if full else (g['grad_' + name + '_head'] if 'grad_' + name + '_head' in g else g['grad_' + name][:32])
         got = (p if full else p[:32]).detach().cpu().numpy()
         # entries whose reference gradient is rounding noise have no defined Adam sign (see test_oracle_golden.py)
         case_p = case[{'user_embeds': 'user_e', 'item_embeds': 'item_e'}[name]].numpy() if name in ('user_embeds', 'item_embeds') else 0.0
