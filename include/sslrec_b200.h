@@ -160,7 +160,8 @@ SSL_API int ssl_bpr_bwd(const float *users, int64_t u_stride, const float *items
  *
  * ssl_rows_normalize  x^ = x / sqrt(1e-8 + |x|^2)  (norm_mode 0, loss_utils.py:33-35) or
  *                     F.normalize(x + 1e-8)        (norm_mode 1, loss_utils.py:45-46) or
- *                     F.normalize(x)               (norm_mode 2, loss_utils.py:78,85);
+ *                     F.normalize(x)               (norm_mode 2, loss_utils.py:78,85) or
+ *                     x itself                     (norm_mode 3: LightGCL contracts raw rows, lightgcl.py:112);
  *   optional gather (idx != NULL: row i of the output is x[idx[i]]), optional scale of the
  *   output (alpha), writes row-major out [n, dim], the K-major tile copy out_t
  *   [ceil(n/64), dim, 64] the streaming side of ssl_softmax_gemm reads (may be NULL),
@@ -208,6 +209,10 @@ SSL_API int ssl_nce_bwd_rows(const float *a_hat, const float *p_hat, const float
  * g_table[j] (+)= rinv_j (dt^_j - t^_j (t^_j . dt^_j)) */
 SSL_API int ssl_nce_bwd_table(const float *dt_part, int32_t n_split, const float *t_hat, const float *rinv, int64_t n,
                       int32_t dim, float *g_table, int64_t g_stride, int32_t accumulate, void *stream);
+/* the epilogue of a term without a positive pair, log(sum_j exp(a_b . t_j / temp) + eps) (lightgcl.py:112-113):
+ * rowsum[b] = sum of the partials + eps, obar = o / rowsum, loss_b[b] = ln(rowsum[b]) */
+SSL_API int ssl_lse_finalize(const float *rowsum_part, const float *o_part, int32_t n_split, int64_t batch, int32_t dim, float eps,
+                     float *rowsum, float *obar, float *loss_b, void *stream);
 /* colscale[b] = scale * (*gscale) * ln2 / rowsum[b] for the swapped gemm */
 SSL_API int ssl_nce_colscale(const float *rowsum, int64_t batch, const float *gscale, float scale, float *colscale, void *stream);
 

@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(256) rows_normalize_kernel(const float *__rest
                 for (int i = 0; i < kMaxPerLane; ++i) if (lane + 32 * i < dim) v[i] += 1e-8f;    // F.normalize(x + 1e-8)
             }
             const float ss = dot_rows(v, v);
-            ri = (mode == 0) ? (1.f / sqrtf(1e-8f + ss)) : (1.f / fmaxf(sqrtf(ss), 1e-12f));
+            ri = (mode == 0) ? (1.f / sqrtf(1e-8f + ss)) : (mode == 3) ? 1.f : (1.f / fmaxf(sqrtf(ss), 1e-12f));   // mode 3: raw rows
             if (lane == 0 && rinv) rinv[row] = ri;
         } else {
 #pragma unroll
@@ -171,6 +171,28 @@ __global__ void nce_finalize_kernel(const float *rowsum_part, const float *o_par
     if (lane == 0) {
         rowsum[b] = rs;
         loss_b[b] = -ap + 1.f / tau + logf(rs);
+    }
+}
+
+// log-sum-exp epilogue without a positive pair (lightgcl.py:112-113): rowsum = sum of the split partials + eps,
+// obar = o / rowsum (the softmax-weighted table average = gradient direction of the anchor), loss_b = log(rowsum)
+__global__ void lse_finalize_kernel(const float *rowsum_part, const float *o_part, int n_split, int64_t batch, int dim, float eps,
+                                    float *rowsum, float *obar, float *loss_b) {
+    const int lane = threadIdx.x & 31;
+    const int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (b >= batch) return;
+    float rs = 0.f;
+    for (int s = 0; s < n_split; ++s) rs += rowsum_part[(size_t)s * batch + b];
+    rs += eps;
+    const float inv = 1.f / rs;
+    for (int k = lane; k < dim; k += 32) {
+        float o = 0.f;
+        for (int s = 0; s < n_split; ++s) o += o_part[((size_t)s * batch + b) * dim + k];
+        obar[b * dim + k] = o * inv;
+    }
+    if (lane == 0) {
+        rowsum[b] = rs;
+        loss_b[b] = logf(rs);
     }
 }
 
@@ -409,7 +431,7 @@ extern "C" int ssl_rows_normalize(const float *x, int64_t stride, const int64_t 
     SSL_CHECK_ARG((out_hi == nullptr) == (out_lo == nullptr) && (out_thi == nullptr) == (out_tlo == nullptr), "ssl_rows_normalize: hi and lo outputs go together");
     SSL_CHECK_ARG(out_thi == nullptr || (t_pitch >= (n + 63) / 64 * 64 && t_pitch % 4 == 0), "ssl_rows_normalize: t_pitch must be >= ceil64(n) and a multiple of 4");
     SSL_CHECK_ARG(dim >= 4 && dim <= SSL_MAX_DIM && dim % 4 == 0, "ssl_rows_normalize: dim %d must be a multiple of 4 <= %d", dim, SSL_MAX_DIM);
-    SSL_CHECK_ARG(norm_mode >= 0 && norm_mode <= 2, "ssl_rows_normalize: bad norm_mode");
+    SSL_CHECK_ARG(norm_mode >= 0 && norm_mode <= 3, "ssl_rows_normalize: bad norm_mode");
     if (n == 0) return SSL_OK;
     const size_t smem = sizeof(float) * 64 * (dim + 1);
     rows_normalize_kernel<<<(unsigned)((n + 63) / 64), 256, smem, STREAM>>>(x, stride, idx, n, dim, norm_mode, alpha, out, out_t, rinv, out_hi, out_lo, out_thi, out_tlo, t_pitch);
@@ -425,6 +447,16 @@ extern "C" int ssl_nce_finalize(const float *rowsum_part, const float *o_part, i
     if (batch == 0) return SSL_OK;
     nce_finalize_kernel<<<(unsigned)((batch + 7) / 8), 256, 0, STREAM>>>(rowsum_part, o_part, n_split, batch, dim, a_hat, p_hat, tau, deno_eps, rowsum, obar, loss_b);
     SSL_LAUNCH_CHECK("nce_finalize_kernel");
+    return SSL_OK;
+}
+
+extern "C" int ssl_lse_finalize(const float *rowsum_part, const float *o_part, int32_t n_split, int64_t batch, int32_t dim, float eps,
+                                float *rowsum, float *obar, float *loss_b, void *stream) {
+    SSL_CHECK_ARG(rowsum_part && o_part && rowsum && obar && loss_b, "ssl_lse_finalize: null argument");
+    SSL_CHECK_ARG(dim >= 1 && dim <= SSL_MAX_DIM && n_split >= 1, "ssl_lse_finalize: bad argument");
+    if (batch == 0) return SSL_OK;
+    lse_finalize_kernel<<<(unsigned)((batch + 7) / 8), 256, 0, STREAM>>>(rowsum_part, o_part, n_split, batch, dim, eps, rowsum, obar, loss_b);
+    SSL_LAUNCH_CHECK("lse_finalize_kernel");
     return SSL_OK;
 }
 

@@ -714,6 +714,88 @@ def infonce_loss_sum(e1: Rows, e2: Rows, table: Rows, idx, temp: float, idx2=Non
     return _InfoNceFn.apply(e1, e2, table, idx, idx2, float(temp), 0, False, 0.0, *_tokens(e1, e2, table))
 
 
+# ---- LightGCL: log-sum-exp of raw (un-normalised) rows against a raw table (lightgcl.py:112-113) -------------
+
+def _raw_operand(x: torch.Tensor, alpha: float, use_tc: bool):
+    """x * alpha with the copies the contraction reads in either role (resident R or streamed C): norm_mode 3."""
+    n, d = x.shape
+    npad = max(64, ceil_to(n, 64))
+    f = dict(device=x.device, dtype=torch.float32)
+    out = torch.empty(npad, d, **f)
+    hi = lo = thi = tlo = out_t = None
+    if use_tc:
+        hi, lo, thi, tlo = torch.empty(npad, d, **f), torch.empty(npad, d, **f), torch.empty(d, npad, **f), torch.empty(d, npad, **f)
+    else:
+        out_t = torch.empty(npad // 64, d, 64, **f)
+    with torch.cuda.device(x.device):
+        check(lib.ssl_rows_normalize(x.data_ptr(), x.stride(0), None, n, d, 3, alpha, out.data_ptr(), _ptr(out_t), None,
+                                     _ptr(hi), _ptr(lo), _ptr(thi), _ptr(tlo), npad, _stream(x)), 'ssl_rows_normalize(raw)')
+    return out, out_t, hi, lo, thi, tlo, npad
+
+
+def _gemm(use_tc, R, n_r, C, n_c, d, colscale, offset, n_split, rs_part, o_part, s, what):
+    """One launch of the contraction in either implementation; R / C are ``_raw_operand`` tuples."""
+    if use_tc:
+        check(lib.ssl_softmax_gemm_tf32x3(R[2].data_ptr(), R[3].data_ptr(), n_r, C[2].data_ptr(), C[3].data_ptr(), C[4].data_ptr(),
+                                          C[5].data_ptr(), C[6], n_c, d, _ptr(colscale), offset, n_split, _ptr(rs_part), o_part.data_ptr(), s), what)
+    else:
+        check(lib.ssl_softmax_gemm(R[0].data_ptr(), n_r, C[0].data_ptr(), C[1].data_ptr(), n_c, d, _ptr(colscale), offset, n_split,
+                                   _ptr(rs_part), o_part.data_ptr(), s), what)
+
+
+class _DenseLseFn(torch.autograd.Function):
+    """mean_b log(sum_j exp(a_b . t_j / temp) + eps) for dense a [B, d], t [n, d] (both receive gradients), without the
+    [B, n] logits: forward = the contraction with R = a log2e / temp, C = t; backward w.r.t. a is its O output, w.r.t. t
+    the swapped contraction.  No running max, as in the reference."""
+
+    @staticmethod
+    def forward(ctx, a, t, temp, eps):
+        _require_cuda(a, 'anchors')
+        _require_cuda(t, 'table')
+        a, t = a.detach().contiguous().float(), t.detach().contiguous().float()
+        (B, d), n = a.shape, t.shape[0]
+        use_tc = USE_TENSOR_CORES and d in (32, 64)
+        A = _raw_operand(a, LOG2E / temp, use_tc)
+        T = _raw_operand(t, 1.0, use_tc)
+        f = dict(device=a.device, dtype=torch.float32)
+        n_split = choose_split((B + 127) // 128, T[6] // 64, slots=148 if use_tc else 296, prefer_few=use_tc)
+        rs_part, o_part = torch.zeros(n_split, B, **f), torch.zeros(n_split, B, d, **f)
+        rowsum, obar, loss_b, out = torch.empty(B, **f), torch.empty(B, d, **f), torch.empty(B, **f), torch.empty((), **f)
+        with torch.cuda.device(a.device):
+            s = _stream(a)
+            with _timed('nce_gemm_fwd', dict(B=B, n=n, dim=d, tc=use_tc)):
+                _gemm(use_tc, A, B, T, n, d, None, 0.0, n_split, rs_part, o_part, s, 'softmax_gemm(lse fwd)')
+            check(lib.ssl_lse_finalize(rs_part.data_ptr(), o_part.data_ptr(), n_split, B, d, eps, rowsum.data_ptr(), obar.data_ptr(),
+                                       loss_b.data_ptr(), s), 'ssl_lse_finalize')
+            check(lib.ssl_sum(loss_b.data_ptr(), B, 1.0 / B, out.data_ptr(), s), 'ssl_sum')
+        ctx.pack = (A, T, B, n, d, temp, use_tc, rowsum, obar)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        A, T, B, n, d, temp, use_tc, rowsum, obar = ctx.pack
+        g = g.contiguous()
+        ga = gt = None
+        if ctx.needs_input_grad[0]:
+            ga = obar * (g * (1.0 / (B * temp)))                 # d/da_b = softmax-weighted table average / (B temp)
+        if ctx.needs_input_grad[1]:
+            f = dict(device=g.device, dtype=torch.float32)
+            colscale = torch.zeros(A[6], **f)
+            n_split = choose_split((n + 127) // 128, A[6] // 64, slots=148 if use_tc else 296, prefer_few=use_tc)
+            dt_part = torch.empty(n_split, n, d, **f)
+            with torch.cuda.device(g.device):
+                s = _stream(g)
+                check(lib.ssl_nce_colscale(rowsum.data_ptr(), B, g.data_ptr(), 1.0 / B, colscale.data_ptr(), s), 'ssl_nce_colscale')
+                with _timed('nce_gemm_bwd', dict(B=B, n=n, dim=d, tc=use_tc)):
+                    _gemm(use_tc, T, n, A, B, d, colscale, 0.0, n_split, None, dt_part, s, 'softmax_gemm(lse bwd)')
+            gt = dt_part[0] if n_split == 1 else dt_part.sum(0)
+        return ga, gt, None, None
+
+
+def dense_logsumexp_mean(a: torch.Tensor, table: torch.Tensor, temp: float, eps: float = 1e-8) -> torch.Tensor:
+    return _DenseLseFn.apply(a, table, float(temp), float(eps))
+
+
 # ---- DirectAU: alignment / uniformity on unit rows (loss_utils.py:75-86) -----------------------------------
 
 def _unit_rows(e: Rows, idx, alpha: float, streamed: bool, use_tc: bool):

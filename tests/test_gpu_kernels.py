@@ -401,3 +401,34 @@ def test_alignment_uniformity_forward_backward(dim, B, use_tc, monkeypatch):
     # the single terms, and the fp32 reference formula (pdist) for the record
     assert abs(LU.uniformity(xs[0].detach()).item() - O.uniformity(x.double()).item()) <= 1e-5
     assert abs(LU.alignment(xs[0].detach(), xs[1].detach()).item() - O.alignment(x.double(), y.double()).item()) <= 1e-5
+
+
+@pytest.mark.parametrize('use_tc', [True, False])
+@pytest.mark.parametrize('dim,B,n', [(64, 1024, 5000), (32, 100, 777), (128, 130, 900), (64, 3, 70)])
+def test_dense_logsumexp_mean_forward_backward(dim, B, n, use_tc, monkeypatch):
+    """LightGCL's mean_b log(sum_j exp(a_b . t_j / temp) + 1e-8) on raw rows (lightgcl.py:112-113) against float64 torch."""
+    from sslrec_b200 import engine
+    monkeypatch.setattr(engine, 'USE_TENSOR_CORES', use_tc)
+    g = torch.Generator().manual_seed(41)
+    a = torch.randn(B, dim, generator=g) * 0.15
+    t = torch.randn(n, dim, generator=g) * 0.15
+    temp = 0.1
+    ins = [x.clone().cuda().requires_grad_(True) for x in (a, t)]
+    out = engine.dense_logsumexp_mean(ins[0], ins[1], temp, 1e-8)
+    (out * 1.7).backward()
+    ref = [x.double().clone().requires_grad_(True) for x in (a, t)]
+    want = torch.log(torch.exp(ref[0] @ ref[1].T / temp).sum(1) + 1e-8).mean()
+    (want * 1.7).backward()
+    assert abs(out.item() - want.item()) <= 1e-5 * max(1.0, abs(want.item())), (out.item(), want.item())
+    for x, r, name in zip(ins, ref, ('anchors', 'table')):
+        H.close(x.grad, r.grad, 2e-4, 2e-5 * r.grad.abs().max().item(), 'grad_' + name)
+    # the anchors may be a gathered, non-leaf slice and the table a slice of a larger tensor, as in the model
+    big = torch.randn(n + 50, dim, generator=g).cuda().requires_grad_(True)
+    idx = torch.randint(0, n, (B,), generator=g).cuda()
+    o2 = engine.dense_logsumexp_mean((big * 0.1)[:n][idx], (big * 0.1)[:n], temp)
+    o2.backward()
+    b64 = big.detach().double().cpu().requires_grad_(True)
+    w2 = torch.log(torch.exp((b64 * 0.1)[:n][idx.cpu()] @ (b64 * 0.1)[:n].T / temp).sum(1) + 1e-8).mean()
+    w2.backward()
+    assert abs(o2.item() - w2.item()) <= 1e-5 * max(1.0, abs(w2.item()))
+    H.close(big.grad, b64.grad, 2e-4, 2e-5 * b64.grad.abs().max().item(), 'grad through slices')

@@ -27,6 +27,16 @@ def _run(model_key, case_name):
     sd = {'user_embeds': case['user_e'], 'item_embeds': case['item_e']}
     if 'user_w' in dr:
         sd['user_hyper_embeds'], sd['item_hyper_embeds'] = dr['user_w'], dr['item_w']
+    if model_key == 'lightgcl':
+        for i, w in enumerate(dr['ws']):
+            sd[f'Ws.{i}.W'] = w
+        # the t.svd_lowrank factors of the reference run (random projections: injected, like every other draw)
+        model.ut, model.vt, model.u_mul_s, model.v_mul_s = (torch.from_numpy(g['svd_' + k]).cuda() for k in ('ut', 'vt', 'u_mul_s', 'v_mul_s'))
+        if 'lgcl_vals' in g:       # R / sqrt(rowD colD): bit-identical values (float32 arithmetic as lightgcl.py:16-20)
+            r, c, v = model._ui
+            o, og = np.lexsort((c, r)), np.lexsort((g['lgcl_cols'], g['lgcl_rows']))
+            assert np.array_equal(r[o], g['lgcl_rows'][og]) and np.array_equal(c[o], g['lgcl_cols'][og])
+            assert np.array_equal(v[o].view(np.uint32), g['lgcl_vals'][og].view(np.uint32))
     model.load_state_dict(sd)
     if model_key == 'ncl':
         model.user_centroids = torch.from_numpy(g['user_centroids']).cuda()

@@ -140,3 +140,18 @@ def test_philox_known_answers_and_sampler_properties():
     u = P.noise_uniform(11, 1, 64, 10)
     assert u.shape == (64, 10) and u.dtype == np.float32 and 0.0 <= u.min() and u.max() < 1.0
     assert abs(P.edge_keep(3, 0, np.arange(20000) % 500, np.arange(20000) // 500, 0.25).mean() - 0.25) < 0.02
+
+
+@pytest.mark.parametrize('case_name', ['tiny', 'small'])
+def test_lightgcl_adjacency_matches_reference_bits(case_name):
+    """R / sqrt(rowD colD) in float32 (lightgcl.py:16-20) as the oracle lays it out: bit-identical to the reference's tensor."""
+    g = replay.load_golden('lightgcl', case_name)
+    case = inputs.make_case(case_name)
+    la = O.lightgcl_adjacency(case['rows'], case['cols'], case['n_user'], case['n_item'])
+    upper = la.rows < la.n_user
+    og = np.lexsort((g['lgcl_cols'], g['lgcl_rows']))
+    assert np.array_equal(la.rows[upper], g['lgcl_rows'][og]) and np.array_equal(la.cols[upper] - la.n_user, g['lgcl_cols'][og])
+    assert np.array_equal(la.vals[upper].view(np.uint32), g['lgcl_vals'][og].view(np.uint32))
+    # the lower block is the transpose: one symmetric CSR serves _spmm(adj, E_i) and _spmm(adj^T, E_u)
+    key, keyt = la.rows * la.n + la.cols, la.cols * la.n + la.rows
+    assert np.array_equal(la.vals[np.argsort(key)].view(np.uint32), la.vals[np.argsort(keyt)].view(np.uint32))
