@@ -41,6 +41,7 @@ WORKLOADS = {
     'lightgcn-xl-8th': ('lightgcn', 'synthetic-xl-8th', dict(layer_num=3, embedding_size=128, reg_weight=1.0e-8, keep_rate=1.0)),
     'ncl-amazon': ('ncl', 'amazon', dict(layer_num=3, embedding_size=64, high_order=2, reg_weight=1.0e-7, proto_weight=1.0e-4,
                                          struct_weight=1.0e-3, temperature=0.1, epoch_period=3, cluster_num=50, keep_rate=1.0)),
+    'lightgcl-gowalla': ('lightgcl', 'gowalla', dict(layer_num=2, embedding_size=64, dropout=0.0, cl_weight=0.1, reg_weight=1.0e-9, temp=0.1, svd_q=5)),
     'directau-gowalla': ('directau', 'gowalla', dict(layer_num=2, embedding_size=64, gamma=2.0)),
     'hccf-amazon': ('hccf', 'amazon', dict(layer_num=2, embedding_size=64, reg_weight=1.0e-7, cl_weight=1.0, temperature=0.1,
                                            keep_rate=0.5, mult=1.0, hyper_num=128, leaky=0.5)),
