@@ -118,7 +118,7 @@ def test_full_predict_topk_match_reference(model_key, case_name):
     assert ok.mean() > 0.9
 
 
-@pytest.mark.parametrize('name', ['lightgcn', 'simgcl', 'ncl'])
+@pytest.mark.parametrize('name', ['lightgcn', 'simgcl', 'ncl', 'directau', 'lightgcl'])
 def test_trainer_epochs_and_evaluate(name):
     """The Trainer mirror end to end on a small graph: train_epoch (sample_negs, DataLoader, cal_loss, backward, FusedAdam,
     asynchronous loss reads), evaluate (full_predict -> native top-k -> recall / ndcg); the loss goes down and the
@@ -132,8 +132,14 @@ def test_trainer_epochs_and_evaluate(name):
     hp = dict(layer_num=2, embedding_size=32, reg_weight=1e-6, keep_rate=0.8, cl_weight=1e-2, temperature=0.2, eps=0.2)
     if name == 'ncl':
         hp.update(high_order=1, proto_weight=1e-3, struct_weight=1e-3, cluster_num=8, epoch_period=1, keep_rate=1.0)
+    if name == 'directau':
+        hp.update(gamma=2.0)
+    if name == 'lightgcl':
+        hp.update(dropout=0.1, temp=0.2, svd_q=5)                # dropout > 0: the in-kernel per-layer value dropout
     cfg = default_config(name, **hp)
     cfg['train'].update(batch_size=1024, epoch=2, loss='pairwise_with_epoch_flag' if name == 'ncl' else 'pairwise')
+    if name in ('directau', 'ncl'):
+        cfg['train']['device_loader'] = True                     # pairs, negative sampling and batching on the device
     cfg['optimizer']['lr'] = 5e-3
     cfg['test']['batch_size'] = 256
     load_config(base=cfg, device='cuda')
