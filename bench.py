@@ -204,7 +204,7 @@ def run_reference(args):
     print(json.dumps({
         'impl': 'reference', 'metric': 'train_steps_per_sec', 'value': val, 'unit': 'steps/s', 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True,
-        'scaling': 'weak' if parallel_mode(args.parallel, args.workload, n_user, n_item, world) == 'dp' else 'strong',
+        'scaling': scaling_label(args.parallel, args.workload, n_user, n_item, world),
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': workload_config(args.workload, n_user, n_item, len(rows), world, parallel_mode(args.parallel, args.workload, n_user, n_item, world)),
         'cpu_baseline': {'value': val, 'unit': 'steps/s', 'cores': threads, 'kind': 'port', 'sample': sample},
@@ -227,6 +227,12 @@ def parallel_mode(requested, name, n_user, n_item, world):
         return requested
     model, _, hp = WORKLOADS[name]
     return 'shard' if (n_user + n_item) * n_views(model) * hp['embedding_size'] * 4 >= (1 << 30) else 'dp'
+
+
+def scaling_label(requested, name, n_user, n_item, world):
+    """'weak' when N > 1 GPUs would each take their own batch (the N = 1 line carries the same label so that the driver's
+    1 -> N series is labelled consistently), 'strong' when one batch is sharded."""
+    return 'weak' if parallel_mode(requested, name, n_user, n_item, max(world, 2)) == 'dp' else 'strong'
 
 
 def workload_config(name, n_user, n_item, n_edge, world, mode='single'):
@@ -516,7 +522,7 @@ def run_ours(args):
     value = units * 1e3 / ms_res
     out = {
         'metric': 'train_steps_per_sec', 'value': value, 'unit': 'steps/s', 'n_gpus': world, 'steps': K, 'warmup': W,
-        'ms_per_step': ms_res, 'higher_is_better': True, 'scaling': 'weak' if mode == 'dp' else 'strong', 'vs_baseline': None, 'dtype': 'f32',
+        'ms_per_step': ms_res, 'higher_is_better': True, 'scaling': scaling_label(args.parallel, args.workload, n_user, n_item, world), 'vs_baseline': None, 'dtype': 'f32',
         'data': 'synthetic', 'config': workload_config(args.workload, n_user, n_item, len(rows), world, mode),
         'batches_per_sync_step': units, 'optimizer_steps_per_sec': 1e3 / ms_res,
         'e2e': {'value': units * 1e3 / ms_e2e, 'unit': 'steps/s', 'ms_per_step': ms_e2e, 'h2d_bytes_per_step': 3 * BATCH * 8,
