@@ -56,6 +56,7 @@ class Adj:
         return int(self.rows.shape[0])
 
     reference_layout: bool = False   # emit COO entries in the reference's (column-sorted) order
+    csr_layout: bool = False         # "tuned CPU" variant of SURVEY.md 8(d): the one-line change adj.to_sparse_csr()
 
     def torch_coo(self, dtype=torch.float32, vals: Optional[torch.Tensor] = None,
                   keep: Optional[np.ndarray] = None) -> torch.Tensor:
@@ -68,7 +69,8 @@ class Adj:
             o = np.lexsort((r, c))
             r, c, v = r[o], c[o], v[torch.from_numpy(o)]
         idx = torch.from_numpy(np.vstack([r, c]).astype(np.int64))
-        return torch.sparse_coo_tensor(idx, v, (self.n, self.n), check_invariants=False)
+        a = torch.sparse_coo_tensor(idx, v, (self.n, self.n), check_invariants=False)
+        return a.coalesce().to_sparse_csr() if self.csr_layout else a
 
     def torch_csr(self, dtype=torch.float32) -> torch.Tensor:
         return self.torch_coo(dtype).coalesce().to_sparse_csr()
@@ -543,7 +545,8 @@ class CpuTrainer:
         self.params = [self.user_e, self.item_e]
         self.opt = torch.optim.Adam(self.params, lr=hp.get('lr', 1e-3), weight_decay=0)
         self.gen = g
-        self.csr = csr
+        if csr:
+            self.adj = Adj(adj.rows, adj.cols, adj.vals, adj.n_user, adj.n_item, csr_layout=True)
 
     def step(self, batch) -> float:
         hp, adj = self.hp, self.adj
