@@ -515,7 +515,8 @@ def run_ours(args):
 
     # ---- CPU baseline on this box's host cores (bounded sample) ----
     cpu = None
-    if not args.no_cpu_baseline and model_name in ('lightgcn', 'simgcl', 'sgl', 'directau'):      # models oracle.CpuTrainer steps
+    # rank 0, N = 1 only (the N > 1 lines of the scaling series carry null); models oracle.CpuTrainer can step
+    if world == 1 and not args.no_cpu_baseline and model_name in ('lightgcn', 'simgcl', 'sgl', 'directau'):
         times, threads = cpu_steps(model_name, hp, rows, cols, n_user, n_item, [b.numpy() for b in host_batches[:3]],
                                    budget_s=45.0, max_steps=2, warmup=1)
         cpu = {'value': 1.0 / float(np.median(times)), 'unit': 'steps/s', 'cores': threads, 'kind': 'port',
