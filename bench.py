@@ -504,7 +504,8 @@ def run_ours(args):
                             'achieved': 3.0 * eq_tf, 'peak': peak, 'unit': 'TFLOP/s', 'frac': 3.0 * eq_tf / peak,
                             'peak_kind': peak_kind + ' cuBLAS bf16 burst / 2 (kind::tf32 issues at half the bf16 rate)',
                             'fp32_equivalent_tflops': eq_tf, 'mma_flop_per_step': 3.0 * nce_flops_step,
-                            'note': 'three tf32 products per fp32-grade product (3xTF32)', 'share_of_step': nce_ms / K / prof_ms}
+                            'note': 'three tf32 products per fp32-grade product (3xTF32)', 'share_of_step': nce_ms / K / prof_ms,
+                            'traffic': ncu_traffic('softmax_gemm_tc_kernel', f'dim{d}_{graph}')}
         else:
             fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
             roofline_nce = {'kernel': 'softmax_gemm_kernel (ssl_softmax_gemm, forward + backward launches)', 'bound': 'fp32_fma', 'achieved': eq_tf,
@@ -546,6 +547,8 @@ def run_ours(args):
         'gpu_launches': launches, 'gpu_launches_per_step': launches / K,
         'embeddings_propagated_per_sec': emb_per_step * value,
         'roofline': roofline, 'roofline_infonce': roofline_nce, 'cpu_baseline': cpu,
+        'roofline_note': 'roofline = the SpMM BASELINE.json names (HBM-bound); roofline_infonce = the kernel with the largest share of this '
+                         'step (tensor-bound contraction); both carry share_of_step',
         'clocks': clocks, 'clocks_e2e': clocks_e2e, 'kernel_ms_per_step': {k: v['ms'] / K for k, v in summ.items()}, 'profiled_ms_per_step': prof_ms,
         'timing_log': timing_log, 'host': {'cpu_count': os.cpu_count(), 'affinity': len(os.sched_getaffinity(0)), 'loadavg': os.getloadavg(),
                                               'usable_cpus': usable_cpus()},
