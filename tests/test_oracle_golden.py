@@ -90,7 +90,7 @@ def test_oracle_reproduces_reference(model_key, case_name):
     assert gap_ok.mean() > 0.9
 
 
-@pytest.mark.parametrize('model_key', ['lightgcn', 'simgcl', 'sgl', 'ncl', 'hccf'])
+@pytest.mark.parametrize('model_key', ['lightgcn', 'simgcl', 'sgl', 'ncl', 'hccf', 'directau', 'lightgcl'])
 def test_float64_replay_bounds_fp32_budget(model_key):
     """loss(fp64) - loss(reference fp32) stays inside the 1e-5 budget of BASELINE.json."""
     g = replay.load_golden(model_key, 'tiny')
