@@ -38,6 +38,7 @@ class HCCF(BaseModel):
         self.edge_drop = EdgeDrop(resize_val=True)
         self._init_runtime(data_handler)
 
+    # ---- pieces of one layer ---------------------------------------------------------------------
     def _gcn_layer(self, embeds, view, layer):
         return E.spmm(self._plan(), embeds, view, layer)
 
@@ -49,43 +50,48 @@ class HCCF(BaseModel):
             return x * keep.to(x.dtype) / keep_rate
         return F.dropout(x, p=1 - keep_rate)
 
+    def _hyper_branch(self, table, incidence, keep_rate, k):
+        """Both sides' hyper-graph message of layer k + 1 (hccf.py:48-49): act(H act(H^T X_side)) with a fresh dropout of H."""
+        nu = self.user_num
+        sides = (table[:nu], table[nu:])
+        out = [self.hgnn_layer(self._dropout(h, keep_rate, k, side), x) for side, (h, x) in enumerate(zip(incidence, sides))]
+        return torch.concat(out, dim=0)
+
     def forward(self, adj, keep_rate):
-        embeds = torch.concat([self.user_embeds, self.item_embeds], dim=0)
-        embeds_list = [embeds]
-        gcn_embeds_list, hyper_embeds_list = [], []
-        uu_hyper = self.user_embeds @ self.user_hyper_embeds * self.mult
-        ii_hyper = self.item_embeds @ self.item_hyper_embeds * self.mult
+        """-> (sum over layers [N, d], per-layer SpMM outputs, per-layer hyper outputs)   (hccf.py:38-54)."""
+        incidence = (self.user_embeds @ self.user_hyper_embeds * self.mult,                    # H_user, H_item (:43-44)
+                     self.item_embeds @ self.item_hyper_embeds * self.mult)
         inj = None if self._inject is None else self._inject.get('edge_masks_per_layer')
-        seed = self._seeds.next()
-        view = self.edge_drop.view(keep_rate, seed, per_layer=True, injected=inj)             # one mask per layer
-        for i in range(self.layer_num):
-            tem_embeds = self._gcn_layer(embeds_list[-1], view, i + 1)
-            hyper_user_embeds = self.hgnn_layer(self._dropout(uu_hyper, keep_rate, i, 0), embeds_list[-1][:self.user_num])
-            hyper_item_embeds = self.hgnn_layer(self._dropout(ii_hyper, keep_rate, i, 1), embeds_list[-1][self.user_num:])
-            gcn_embeds_list.append(tem_embeds)
-            hyper_embeds_list.append(torch.concat([hyper_user_embeds, hyper_item_embeds], dim=0))
-            embeds_list.append(tem_embeds + hyper_embeds_list[-1])
-        embeds = sum(embeds_list)
-        return embeds, gcn_embeds_list, hyper_embeds_list
+        view = self.edge_drop.view(keep_rate, self._seeds.next(), per_layer=True, injected=inj)   # a fresh rescaled mask per layer (:47)
+        layers = [torch.concat([self.user_embeds, self.item_embeds], dim=0)]
+        gcn_out, hyper_out = [], []
+        for k in range(self.layer_num):
+            gcn_out.append(self._gcn_layer(layers[-1], view, k + 1))
+            hyper_out.append(self._hyper_branch(layers[-1], incidence, keep_rate, k))
+            layers.append(gcn_out[-1] + hyper_out[-1])                                         # :52
+        return sum(layers), gcn_out, hyper_out
+
+    def _contrast(self, gcn_out, hyper_out, ancs, poss):
+        """sum over layers and sides of the spec-node InfoNCE between the DETACHED SpMM output and the hyper output on the
+        batch's unique users / items (hccf.py:76-81)."""
+        nu = self.user_num
+        picks = ((slice(0, nu), torch.unique(ancs)), (slice(nu, None), torch.unique(poss)))
+        total = 0
+        for g, h in zip(gcn_out, hyper_out):
+            g = g.detach()
+            for rows, nodes in picks:
+                total = total + cal_infonce_loss_spec_nodes(g[rows], h[rows], nodes, self.temperature)
+        return total
 
     def cal_loss(self, batch_data):
         ancs, poss, negs = batch_data
-        embeds, gcn_embeds_list, hyper_embeds_list = self.forward(self.adj, self.keep_rate)
-        user_embeds, item_embeds = embeds[:self.user_num], embeds[self.user_num:]
+        embeds, gcn_out, hyper_out = self.forward(self.adj, self.keep_rate)
+        users, items = embeds[:self.user_num], embeds[self.user_num:]
         # -log sigmoid(a.p - a.n).mean() == softplus(a.n - a.p).mean()  (hccf.py:70-74)
-        bpr_loss = cal_bpr_loss(user_embeds[ancs], item_embeds[poss], item_embeds[negs]) / ancs.shape[0]
-        cl_loss = 0
-        ua, up = torch.unique(ancs), torch.unique(poss)
-        for i in range(self.layer_num):
-            embeds1 = gcn_embeds_list[i].detach()
-            embeds2 = hyper_embeds_list[i]
-            cl_loss = cl_loss + cal_infonce_loss_spec_nodes(embeds1[:self.user_num], embeds2[:self.user_num], ua, self.temperature) + \
-                cal_infonce_loss_spec_nodes(embeds1[self.user_num:], embeds2[self.user_num:], up, self.temperature)
-        reg_loss = reg_params(self) * self.reg_weight
-        cl_loss = cl_loss * self.cl_weight
-        loss = bpr_loss + reg_loss + cl_loss
-        losses = {'bpr_loss': bpr_loss, 'reg_loss': reg_loss, 'cl_loss': cl_loss}
-        return loss, losses
+        terms = {'bpr_loss': cal_bpr_loss(users[ancs], items[poss], items[negs]) / ancs.shape[0],
+                 'reg_loss': reg_params(self) * self.reg_weight,
+                 'cl_loss': self._contrast(gcn_out, hyper_out, ancs, poss) * self.cl_weight}
+        return terms['bpr_loss'] + terms['reg_loss'] + terms['cl_loss'], terms
 
     def full_predict(self, batch_data):
         embeds, _, _ = self.forward(self.adj, 1.0)

@@ -1,0 +1,82 @@
+"""Host-side logic of the autograd-composed drop-ins (HCCF, LightGCL) on CPU: the three native entry points they call are
+replaced by the oracle's torch restatements, so the Python composition (layer loop, dropout injection, loss terms, their
+order and weights, the parameters that receive gradients) is checked against the reference's golden vectors without a GPU.
+The kernels themselves are covered by the -m gpu tests."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import cf_oracle as O
+from oracle import inputs, replay
+import ssl_test_helpers as H
+
+
+def _close(a, b, rtol, atol, what):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    err = np.abs(a - b)
+    assert (err <= atol + rtol * np.abs(b) + 2e-6 * np.abs(b).max()).all(), f'{what}: max err {err.max():.3e}'
+
+
+def _setup(model_key):
+    g = replay.load_golden(model_key, 'tiny')
+    case = inputs.make_case('tiny')
+    adj = O.normalized_adjacency(case['rows'], case['cols'], case['n_user'], case['n_item'])
+    dr = replay.draws(model_key, case, g['hp'], adj)
+    return g, case, adj, dr
+
+
+def test_hccf_composition_matches_reference_on_cpu(monkeypatch):
+    from sslrec_b200.general_cf import hccf as M
+    g, case, adj, dr = _setup('hccf')
+    hp = g['hp']
+    inject = {'edge_masks_per_layer': [torch.from_numpy(m.astype(np.uint8)) for m in dr['edge_keeps']], 'hyper_keeps': dr['hyper_keeps']}
+    model, _ = H.make_model('hccf', case, hp, inject=inject, device='cpu')
+    model.load_state_dict({'user_embeds': case['user_e'], 'item_embeds': case['item_e'],
+                           'user_hyper_embeds': dr['user_w'], 'item_hyper_embeds': dr['item_w']})
+
+    def gcn_layer(embeds, view, layer):                       # stands in for engine.spmm (ssl_propagate_layer)
+        assert view.edge_mode == 2 and abs(view.scale - 1.0 / hp['keep_rate']) < 1e-12
+        mask = view.edge_mask_for(layer).numpy().astype(bool)
+        return torch.sparse.mm(O.edge_dropped(adj, mask, hp['keep_rate'], True, embeds.dtype), embeds)
+    monkeypatch.setattr(model, '_gcn_layer', gcn_layer)
+    monkeypatch.setattr(M, 'cal_bpr_loss', O.bpr_loss_sum)
+    monkeypatch.setattr(M, 'cal_infonce_loss_spec_nodes', O.infonce_spec_nodes_mean)
+    batch = [torch.from_numpy(case[k]) for k in ('ancs', 'poss', 'negs')]
+    loss, parts = model.cal_loss(batch)
+    assert list(parts) == ['bpr_loss', 'reg_loss', 'cl_loss']
+    _close(loss.item(), g['loss'], 2e-6, 1e-7, 'loss')
+    for k, v in parts.items():
+        _close(float(v), g['part_' + k], 2e-6, 1e-9, k)
+    loss.backward()
+    for name, p in model.named_parameters():
+        _close(p.grad, g['grad_' + name], 1e-4, 1e-9, 'grad_' + name)
+
+
+def test_lightgcl_composition_matches_reference_on_cpu(monkeypatch):
+    from sslrec_b200.general_cf import lightgcl as M
+    from sslrec_b200 import engine as E
+    g, case, adj, dr = _setup('lightgcl')
+    hp = g['hp']
+    model, _ = H.make_model('lightgcl', case, hp, device='cpu')
+    sd = {'user_embeds': case['user_e'], 'item_embeds': case['item_e']}
+    sd.update({f'Ws.{i}.W': w for i, w in enumerate(dr['ws'])})
+    model.load_state_dict(sd)
+    model.ut, model.vt, model.u_mul_s, model.v_mul_s = (torch.from_numpy(g['svd_' + k]) for k in ('ut', 'vt', 'u_mul_s', 'v_mul_s'))
+    ladj = O.lightgcl_adjacency(case['rows'], case['cols'], case['n_user'], case['n_item'])
+    r, c, v = model._ui                                        # the model's own R / sqrt(rowD colD): bit-identical to the reference's
+    o, og = np.lexsort((c, r)), np.lexsort((g['lgcl_cols'], g['lgcl_rows']))
+    assert np.array_equal(v[o].view(np.uint32), g['lgcl_vals'][og].view(np.uint32))
+    monkeypatch.setattr(model, '_bipartite_plan', lambda: None)
+    monkeypatch.setattr(E, 'spmm', lambda plan, x, view, layer: torch.sparse.mm(ladj.torch_coo(x.dtype), x))
+    monkeypatch.setattr(M, 'cal_bpr_loss', O.bpr_loss_sum)
+    monkeypatch.setattr(E, 'dense_logsumexp_mean',
+                        lambda a, t, temp, eps=1e-8: torch.log(torch.exp(a @ t.T / temp).sum(1) + eps).mean())
+    batch = [torch.from_numpy(case[k]) for k in ('ancs', 'poss', 'negs')]
+    loss, parts = model.cal_loss(batch)
+    _close(loss.item(), g['loss'], 2e-6, 1e-7, 'loss')
+    for k, val in parts.items():
+        _close(float(val), g['part_' + k], 2e-6, 1e-9, k)
+    loss.backward()
+    for name, p in model.named_parameters():
+        _close(p.grad, g['grad_' + name], 1e-4, 1e-9, 'grad_' + name)
+    assert set(model.state_dict()) == {'user_embeds', 'item_embeds', 'Ws.0.W', 'Ws.1.W'}
