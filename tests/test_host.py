@@ -117,3 +117,29 @@ def test_batch_shard_coalesce_orders_by_parameter_position():
         assert [x.numel() for x in bufs] == want, [x.numel() for x in bufs]
     nc = torch.zeros(4, 6)[:, :3]                                 # non-contiguous gradients travel alone
     assert [x.numel() for x in BatchShard.coalesce([nc, a])] == [12, 12]
+
+
+def test_device_loader_shares_and_flags_with_a_stub_dataset():
+    """DeviceLoader's shuffling / sharding / epoch-flag bookkeeping is device-agnostic: exercised here with a CPU stub in
+    place of DeviceTrnData (whose kernels are covered by the GPU tests)."""
+    from sslrec_b200.data_handler import DeviceLoader, DeviceTrnData
+
+    class Stub:
+        device, epoch_period, epoch_flag_counter = torch.device('cpu'), 2, -1
+        rows = torch.arange(103) * 10
+        cols = negs = torch.arange(103)
+        __len__ = lambda self: 103
+        batch = DeviceTrnData.batch
+    full = DeviceLoader(Stub(), 16, seed=3)
+    assert len(full) == 7
+    got = torch.cat([b[0] for b in full])
+    assert sorted(got.tolist()) == (torch.arange(103) * 10).tolist()
+    first, second = torch.cat([b[0] for b in full]), torch.cat([b[0] for b in full])
+    assert not torch.equal(first, second)                          # a fresh permutation per epoch
+    shares = [torch.cat([b[0] for b in DeviceLoader(Stub(), 16, rank=r, world=3, seed=5)]) for r in range(3)]
+    assert [len(s) for s in shares] == [35, 35, 35] and len(DeviceLoader(Stub(), 16, rank=0, world=3)) == 3
+    assert set(torch.cat(shares).tolist()) == set((torch.arange(103) * 10).tolist())    # padded by wrap-around, nothing lost
+    ds = Stub()
+    loader = DeviceLoader(ds, 16, seed=4)
+    flags = [int(torch.cat([b[3] for b in loader]).sum()) for _ in range(5)]
+    assert flags == [1, 1, 0, 1, 0]                                # first sample ever, then pair 0 on every 2nd visit
