@@ -4,7 +4,7 @@
 
 One "step" = one iteration of trainer/trainer.py:63-68 (zero_grad, cal_loss, backward, Adam step) at
 B = 4096 on BASELINE.json configs[1]: SimGCL, d = 64, L = 3, tau = 0.2, on a synthetic graph with the
-reference's amazon shape (|U| = 76 469, |I| = 83 761, nnz = 2 x 966 680; sslrec_b200/datagen.py).
+reference's amazon shape (|U| = 76 469, |I| = 83 761, nnz = 2 x 966 680; synth_graphs.py).
 Prints ONE JSON line (contract in the task statement):
   value      steps/s with the batch indices already resident in HBM (CUDA events, max over ranks)
   e2e        steps/s through the plugin surface from pinned HOST index buffers, with the H2D copy of
@@ -38,6 +38,8 @@ WORKLOADS = {
     'lightgcn-gowalla': ('lightgcn', 'gowalla', dict(layer_num=3, embedding_size=64, reg_weight=1.0e-8, keep_rate=0.5)),
     'sgl-yelp': ('sgl', 'yelp', dict(layer_num=3, embedding_size=64, temperature=0.2, cl_weight=1.0, reg_weight=1.0e-5,
                                      keep_rate=0.5, augmentation='edge_drop')),
+    # BASELINE.json configs[3]: row-sharded over the GPUs (bench_rowshard.py); the whole 10 M x 2 M / 300 M-edge graph at any N
+    'lightgcn-xl': ('lightgcn', 'synthetic-xl', dict(layer_num=3, embedding_size=128, reg_weight=1.0e-8, keep_rate=1.0)),
     'lightgcn-xl-8th': ('lightgcn', 'synthetic-xl-8th', dict(layer_num=3, embedding_size=128, reg_weight=1.0e-8, keep_rate=1.0)),
     'ncl-amazon': ('ncl', 'amazon', dict(layer_num=3, embedding_size=64, high_order=2, reg_weight=1.0e-7, proto_weight=1.0e-4,
                                          struct_weight=1.0e-3, temperature=0.1, epoch_period=3, cluster_num=50, keep_rate=1.0)),
@@ -54,7 +56,7 @@ def rank_world():
 
 
 def graph_arrays(name):
-    from sslrec_b200.datagen import named_graph
+    from synth_graphs import named_graph
     cache = os.path.join('/tmp', f'sslrec_b200_graph_{name}.npz')
     if os.path.exists(cache):
         z = np.load(cache)
@@ -187,31 +189,94 @@ def cpu_steps(model, hp, rows, cols, n_user, n_item, batches, budget_s, max_step
     return times, threads
 
 
+def reference_available():
+    """The unmodified reference, vendored to oracle/_ref by oracle/vendor_ref.py (build() runs the recipe)."""
+    try:
+        from oracle import vendor_ref
+        return vendor_ref.available() or os.path.isdir(vendor_ref.REF)
+    except Exception:      # noqa: BLE001
+        return False
+
+
+def reference_steps(model, hp, rows, cols, n_user, n_item, batches, budget_s, max_steps, warmup=1, csr=False, threads=None):
+    """Seconds per step of the reference's CPU path on this box's host cores: the UNMODIFIED reference (oracle/_ref,
+    kind "reference") when it is there, else the oracle port (kind "port")."""
+    if reference_available() and model in ('lightgcn', 'simgcl', 'sgl', 'ncl', 'hccf', 'directau', 'lightgcl'):
+        from oracle import ref_runner
+        cands = [threads] if threads else sorted({usable_cpus(), min(usable_cpus(), 32)}, reverse=True)
+        times, used = ref_runner.time_steps(model, rows, cols, n_user, n_item, hp, batches, cands, budget_s, max_steps, warmup=warmup, csr=csr)
+        return times, used, 'reference'
+    times, used = cpu_steps(model, hp, rows, cols, n_user, n_item, batches, budget_s, max_steps, warmup=warmup, csr=csr, threads=threads)
+    return times, used, 'port'
+
+
 def run_reference(args):
+    """The reference arm: no GPU work and nothing of sslrec_b200 is imported in this process."""
     rank, _, world = rank_world()
     if rank != 0:
         return
     model, graph, hp = WORKLOADS[args.workload]
-    if model not in ('lightgcn', 'simgcl', 'sgl', 'directau'):
-        print(json.dumps({'impl': 'reference', 'unavailable': f'oracle.CpuTrainer has no whole-step driver for {model} (per-call oracle only)'}))
+    if not reference_available() and model not in ('lightgcn', 'simgcl', 'sgl', 'directau'):
+        print(json.dumps({'impl': 'reference', 'unavailable': f'oracle/_ref is absent and oracle.CpuTrainer has no whole-step driver for {model}'}))
+        return
+    if graph.startswith('synthetic-xl'):
+        print(json.dumps({'impl': 'reference', 'unavailable': 'config 4 (600 M stored entries) does not fit the bounded CPU sample; see cpu_baseline of lightgcn-xl-8th'}))
         return
     rows, cols, n_user, n_item = graph_arrays(graph)
     batches = make_batches(rows, cols, n_item, max(2, min(args.steps + args.warmup, 8)))
-    times, threads = cpu_steps(model, hp, rows, cols, n_user, n_item, batches, budget_s=170.0, max_steps=args.steps,
-                               warmup=min(args.warmup, 1))
+    times, threads, kind = reference_steps(model, hp, rows, cols, n_user, n_item, batches, budget_s=args.cpu_budget, max_steps=args.steps,
+                                           warmup=max(1, min(args.warmup, 2)), csr=args.cpu_csr)
     ms = 1e3 * float(np.median(times))
     val = 1e3 / ms
-    sample = (f'{len(times)} of {args.steps} full training steps executed inside the 170 s budget (median step time); '
-              f'oracle port of the reference CPU path (torch {torch.__version__} sparse COO spmm + dense InfoNCE), {threads} threads')
+    what = ('the unmodified reference (oracle/_ref: build_data_handler, build_model, Trainer.create_optimizer, the trainer.py:63-68 loop)'
+            if kind == 'reference' else 'oracle port of the reference CPU path')
+    sample = (f'{len(times)} of {args.steps} full training steps executed inside the {args.cpu_budget:.0f} s budget (median step time); '
+              f'{what}, torch {torch.__version__} sparse {"CSR" if args.cpu_csr else "COO"} spmm + dense InfoNCE, {threads} threads')
     print(json.dumps({
         'impl': 'reference', 'metric': 'train_steps_per_sec', 'value': val, 'unit': 'steps/s', 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True,
         'scaling': scaling_label(args.parallel, args.workload, n_user, n_item, world),
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': workload_config(args.workload, n_user, n_item, len(rows), world, parallel_mode(args.parallel, args.workload, n_user, n_item, world)),
-        'cpu_baseline': {'value': val, 'unit': 'steps/s', 'cores': threads, 'kind': 'port', 'sample': sample},
+        'cpu_baseline': {'value': val, 'unit': 'steps/s', 'cores': threads, 'kind': kind, 'sample': sample},
         'e2e': {'value': val, 'unit': 'steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'sslrec_b200_imported': 'sslrec_b200' in sys.modules,
     }))
+
+
+def cpu_baseline_subprocess(workload, steps, budget_s, csr=False):
+    """The cpu_baseline leg of the GPU arm: the reference arm in its own process (the reference's config is a module-level
+    singleton and its harness shims torch.Tensor.cuda -- neither belongs in the process that measures the GPU)."""
+    cmd = [sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--workload', workload, '--steps', str(steps), '--warmup', '1',
+           '--cpu-budget', str(budget_s)] + (['--cpu-csr'] if csr else [])
+    env = {k: v for k, v in os.environ.items() if k not in ('RANK', 'LOCAL_RANK', 'WORLD_SIZE')}
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=budget_s * 4 + 120, env=env)
+    for line in reversed(r.stdout.strip().splitlines()):
+        if line.startswith('{'):
+            return json.loads(line)
+    raise RuntimeError('reference arm printed no JSON line: ' + r.stderr[-400:])
+
+
+class Watchdog:
+    """If the optional row-shard leg wedges (a rank died inside a collective), still deliver the bench line: after
+    ``deadline_s`` the fallback is printed by rank 0 and every rank leaves with exit code 0."""
+
+    def __init__(self, deadline_s, fallback):
+        self.timer = threading.Timer(deadline_s, self._fire)
+        self.timer.daemon = True
+        self.fallback = fallback
+        self.timer.start()
+
+    def _fire(self):
+        try:
+            line = self.fallback()
+            if line is not None:
+                print(line, flush=True)
+        finally:
+            os._exit(0)
+
+    def cancel(self):
+        self.timer.cancel()
 
 
 def n_views(model):
@@ -400,22 +465,23 @@ def run_ours(args):
     barrier()
     # the value is timed WITHOUT NVML traffic (sampling while a sub-millisecond-per-step workload runs stalls the GPU:
     # lightgcn-gowalla read 6.6 ms/step sampled vs 0.7 ms unsampled); the clocks come from an immediate sampled replay
-    # Three passes of exactly K steps each; the value is the least-perturbed (fastest) pass and every pass is listed in
-    # timing_log.  The GPU work is deterministic; what varies is the host: the boxes are shared and cgroup-limited
-    # (r01: a pass read 8.7 ms/step where its neighbours read 2.9 ms with identical kernels, see profiles/r01d_*).
-    passes = [timed(step_resident, no_sampling=True) for _ in range(3)]
-    ms_res, launches, _ = min(passes, key=lambda p: p[0])
+    # Three passes of exactly K steps each; the value is the MEDIAN pass and every pass is listed in timing_log.  The GPU
+    # work is deterministic; what varies is the host: the boxes are shared and cgroup-limited (r01: a pass read
+    # 8.7 ms/step where its neighbours read 2.9 ms with identical kernels, see profiles/r01d_*).
+    passes = sorted((timed(step_resident, no_sampling=True) for _ in range(3)), key=lambda p: p[0])
+    ms_res, launches, _ = passes[1]                      # the MEDIAN pass is the value; all three are in timing_log
+    ms_res_best = passes[0][0]
     ms_res_sampled, _, clocks = timed(step_resident, steps=max(K, 60))      # long enough for several NVML samples
     if clocks is not None:
         clocks['sampled_replay_ms_per_step'] = ms_res_sampled
     # e2e is timed WITHOUT clock sampling (one NVML sample costs ~14 ms of host time, which the per-step
     # syncs of this loop would expose); its clocks come from a short sampled replay of the same loop
-    ms_e2e_strict = min(timed(step_e2e, no_sampling=True)[0] for _ in range(2))
+    ms_e2e_strict = float(np.median([timed(step_e2e, no_sampling=True)[0] for _ in range(3)]))
 
     def timed_async():
         ms, _, _ = timed(step_e2e_async, no_sampling=True, tail=lambda: seen.__setitem__(0, seen[0] + len(reader.flush())))
         return ms
-    ms_e2e = min(timed_async() for _ in range(3))
+    ms_e2e = float(np.median([timed_async() for _ in range(3)]))
     _, _, clocks_e2e = timed(step_e2e, inline_sampling=True, steps=min(K, 6))
 
     # ---- live kernel timings (CUDA events on the launching stream) over K more steps ----
@@ -434,126 +500,213 @@ def run_ours(args):
     if os.environ.get('BENCH_DIAG'):
         timed(step_resident, no_sampling=True)
         timed(step_e2e, no_sampling=True)
-    if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
-        return
 
-    # ---- one real epoch through Trainer.train_epoch (sample_negs + loader + loop), device loader vs host DataLoader ----
-    epoch = None
-    if world == 1 and model_name != 'ncl' and len(rows) // BATCH <= 1000:
-        import types
-        from sslrec_b200.data_handler import DeviceLoader, DeviceTrnData
-        from sslrec_b200.trainer import Trainer
-        epoch = {'batches': (len(rows) + BATCH - 1) // BATCH,
-                 'how': 'wall clock of Trainer.train_epoch (negative sampling, shuffling, batching, H2D, steps, loss reads), after one warm-up epoch'}
-        for key, loader in (('device_loader', DeviceLoader(DeviceTrnData(trn, dev, 2023), BATCH)), ('host_dataloader', dh.train_dataloader)):
-            tr = Trainer(types.SimpleNamespace(train_dataloader=loader))
-            tr.optimizer = opt
-            best = None
-            for rep in range(3 if key == 'device_loader' else 2):
-                torch.cuda.synchronize()
-                t0 = time.perf_counter()
-                tr.train_epoch(model, rep)
-                torch.cuda.synchronize()
-                dt = time.perf_counter() - t0
-                best = dt if (best is None or rep == 1) else min(best, dt)      # rep 0 is the warm-up
-            epoch[key + '_steps_per_sec'] = len(loader) / best
-            epoch[key + '_epoch_s'] = best
+    def assemble():
+        """Rank 0: everything of the bench line except the row-shard record."""
+        # ---- one real epoch through Trainer.train_epoch (sample_negs + loader + loop), device loader vs host DataLoader ----
+        epoch = None
+        if world == 1 and model_name != 'ncl' and len(rows) // BATCH <= 1000:
+            import types
+            from sslrec_b200.data_handler import DeviceLoader, DeviceTrnData
+            from sslrec_b200.trainer import Trainer
+            epoch = {'batches': (len(rows) + BATCH - 1) // BATCH,
+                     'how': 'wall clock of Trainer.train_epoch (negative sampling, shuffling, batching, H2D, steps, loss reads), after one warm-up epoch'}
+            for key, loader in (('device_loader', DeviceLoader(DeviceTrnData(trn, dev, 2023), BATCH)), ('host_dataloader', dh.train_dataloader)):
+                tr = Trainer(types.SimpleNamespace(train_dataloader=loader))
+                tr.optimizer = opt
+                best = None
+                for rep in range(3 if key == 'device_loader' else 2):
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    tr.train_epoch(model, rep)
+                    torch.cuda.synchronize()
+                    dt = time.perf_counter() - t0
+                    best = dt if (best is None or rep == 1) else min(best, dt)      # rep 0 is the warm-up
+                epoch[key + '_steps_per_sec'] = len(loader) / best
+                epoch[key + '_epoch_s'] = best
 
-    peaks, peak_kind = measured_peaks()
-    N, nnz, d = n_user + n_item, 2 * len(rows), hp['embedding_size']
-    L = hp['layer_num']
-    views = n_views(model_name)
-    launches_all = engine_launches
+        peaks, peak_kind = measured_peaks()
+        N, nnz, d = n_user + n_item, 2 * len(rows), hp['embedding_size']
+        L = hp['layer_num']
+        views = n_views(model_name)
+        launches_all = engine_launches
 
-    def prop_alg_bytes(m):
-        """Algorithmic bytes of one propagation launch: per stored entry its (col, val) pair
-        (8 B) and one d-wide row per gathered view (4 d B); per output row its work item (16 B), every d-wide
-        row the epilogue must read (residual, layer-sum sources, regulariser row) and every row it writes."""
-        row = 4 * m['dim']
-        b = m['nnz'] * (8 + row * m['gather_views'])
-        per_row = 16 + (row * m['views'] if m['residual'] else 0) + sum(row * sv for sv in m['sum_src']) + (row if m['reg_src'] else 0)
-        per_row += row * m['views'] if m['x_out'] else 0
-        per_row += (row if m['reduce_views'] else row * m['views']) if m['sum_out'] else 0
-        return b + m['rows'] * per_row
-    prop = [(m, ms) for name, m, ms in launches_all if name in ('prop_fwd', 'prop_bwd')]
-    prop_ms = sum(ms for _, ms in prop)
-    prop_bytes = sum(prop_alg_bytes(m) for m, _ in prop)
-    achieved = prop_bytes / (prop_ms * 1e-3) / 1e9 if prop else None
-    roofline = {'kernel': 'prop_kernel (ssl_propagate_layer; all forward + transposed-backward launches of the timed steps)',
-                'bound': 'hbm', 'achieved': achieved, 'peak': peaks['hbm_gbs'], 'peak_kind': peak_kind + ' (burst copy)', 'unit': 'GB/s',
-                'frac': (achieved / peaks['hbm_gbs']) if achieved else None, 'traffic': ncu_traffic('prop_kernel', f'views{views}_dim{d}_{graph}'),
-                'avg_launch_ms': prop_ms / len(prop) if prop else None, 'alg_bytes_per_launch': prop_bytes / len(prop) if prop else None,
-                'launches_per_step': len(prop) / K, 'share_of_step': prop_ms / K / prof_ms if prof_ms else None,
-                'note': 'the 41 MB/view tables of this graph fit the 126 MB L2, so achieved counts L2 hits and can exceed the HBM peak; '
-                        'traffic (ncu dram bytes) is in profiles/'}
-    # the dense InfoNCE contraction (not HBM-bound): on the tcgen05 tensor cores with 3xTF32 error compensation when
-    # dim is 32 / 64, else on the FP32 FMA pipe
-    nce = [(m, ms) for name, m, ms in launches_all if name in ('nce_gemm_fwd', 'nce_gemm_bwd')]
-    nce_ms = sum(ms for _, ms in nce)
-    nce_flops_step = sum(4.0 * m['B'] * m['n'] * m['dim'] for m, _ in nce) / K          # fp32-equivalent: S = R C^T and O += E C
-    sm_mhz = (clocks or {}).get('sm_mhz') or 1965.0
-    roofline_nce = None
-    if nce:
-        used_tc = all(m.get('tc') for m, _ in nce)
-        eq_tf = nce_flops_step * K / (nce_ms * 1e-3) / 1e12
-        if used_tc:
-            peak = peaks['bf16_tflops'] / 2.0
-            roofline_nce = {'kernel': 'softmax_gemm_tc_kernel (ssl_softmax_gemm_tf32x3, forward + backward launches)', 'bound': 'tensor',
-                            'achieved': 3.0 * eq_tf, 'peak': peak, 'unit': 'TFLOP/s', 'frac': 3.0 * eq_tf / peak,
-                            'peak_kind': peak_kind + ' cuBLAS bf16 burst / 2 (kind::tf32 issues at half the bf16 rate)',
-                            'fp32_equivalent_tflops': eq_tf, 'mma_flop_per_step': 3.0 * nce_flops_step,
-                            'note': 'three tf32 products per fp32-grade product (3xTF32)', 'share_of_step': nce_ms / K / prof_ms,
-                            'traffic': ncu_traffic('softmax_gemm_tc_kernel', f'dim{d}_{graph}')}
-        else:
-            fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
-            roofline_nce = {'kernel': 'softmax_gemm_kernel (ssl_softmax_gemm, forward + backward launches)', 'bound': 'fp32_fma', 'achieved': eq_tf,
-                            'peak': fp32_peak, 'peak_kind': f'148 SM x 128 FMA/clk x 2 x {sm_mhz:.0f} MHz', 'unit': 'TFLOP/s',
-                            'frac': eq_tf / fp32_peak, 'flop_per_step': nce_flops_step, 'share_of_step': nce_ms / K / prof_ms}
-    n_prop_layers = max(L, 2 * hp.get('high_order', 0))
-    emb_per_step = 2.0 * views * n_prop_layers * nnz if model_name != 'sgl' else 2.0 * L * nnz * (1 + 2 * hp['keep_rate'])
+        def prop_alg_bytes(m):
+            """Algorithmic bytes of one propagation launch: per stored entry its (col, val) pair
+            (8 B) and one d-wide row per gathered view (4 d B); per output row its work item (16 B), every d-wide
+            row the epilogue must read (residual, layer-sum sources, regulariser row) and every row it writes."""
+            row = 4 * m['dim']
+            b = m['nnz'] * (8 + row * m['gather_views'])
+            per_row = 16 + (row * m['views'] if m['residual'] else 0) + sum(row * sv for sv in m['sum_src']) + (row if m['reg_src'] else 0)
+            per_row += row * m['views'] if m['x_out'] else 0
+            per_row += (row if m['reduce_views'] else row * m['views']) if m['sum_out'] else 0
+            return b + m['rows'] * per_row
+        prop = [(m, ms) for name, m, ms in launches_all if name in ('prop_fwd', 'prop_bwd')]
+        prop_ms = sum(ms for _, ms in prop)
+        prop_bytes = sum(prop_alg_bytes(m) for m, _ in prop)
+        achieved = prop_bytes / (prop_ms * 1e-3) / 1e9 if prop else None
+        roofline = {'kernel': 'prop_kernel (ssl_propagate_layer; all forward + transposed-backward launches of the timed steps)',
+                    'bound': 'hbm', 'achieved': achieved, 'peak': peaks['hbm_gbs'], 'peak_kind': peak_kind + ' (burst copy)', 'unit': 'GB/s',
+                    'frac': (achieved / peaks['hbm_gbs']) if achieved else None, 'traffic': ncu_traffic('prop_kernel', f'views{views}_dim{d}_{graph}'),
+                    'avg_launch_ms': prop_ms / len(prop) if prop else None, 'alg_bytes_per_launch': prop_bytes / len(prop) if prop else None,
+                    'launches_per_step': len(prop) / K, 'share_of_step': prop_ms / K / prof_ms if prof_ms else None,
+                    'note': 'the 41 MB/view tables of this graph fit the 126 MB L2, so achieved counts L2 hits and can exceed the HBM peak; '
+                            'traffic (ncu dram bytes) is in profiles/'}
+        # the dense InfoNCE contraction (not HBM-bound): on the tcgen05 tensor cores with 3xTF32 error compensation when
+        # dim is 32 / 64, else on the FP32 FMA pipe
+        nce = [(m, ms) for name, m, ms in launches_all if name in ('nce_gemm_fwd', 'nce_gemm_bwd')]
+        nce_ms = sum(ms for _, ms in nce)
+        nce_flops_step = sum(4.0 * m['B'] * m['n'] * m['dim'] for m, _ in nce) / K          # fp32-equivalent: S = R C^T and O += E C
+        sm_mhz = (clocks or {}).get('sm_mhz') or 1965.0
+        roofline_nce = None
+        if nce:
+            used_tc = all(m.get('tc') for m, _ in nce)
+            eq_tf = nce_flops_step * K / (nce_ms * 1e-3) / 1e12
+            if used_tc:
+                peak = peaks['bf16_tflops'] / 2.0
+                roofline_nce = {'kernel': 'softmax_gemm_tc_kernel (ssl_softmax_gemm_tf32x3, forward + backward launches)', 'bound': 'tensor',
+                                'achieved': 3.0 * eq_tf, 'peak': peak, 'unit': 'TFLOP/s', 'frac': 3.0 * eq_tf / peak,
+                                'peak_kind': peak_kind + ' cuBLAS bf16 burst / 2 (kind::tf32 issues at half the bf16 rate)',
+                                'fp32_equivalent_tflops': eq_tf, 'mma_flop_per_step': 3.0 * nce_flops_step,
+                                'note': 'three tf32 products per fp32-grade product (3xTF32)', 'share_of_step': nce_ms / K / prof_ms,
+                                'traffic': ncu_traffic('softmax_gemm_tc_kernel', f'dim{d}_{graph}')}
+            else:
+                fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
+                roofline_nce = {'kernel': 'softmax_gemm_kernel (ssl_softmax_gemm, forward + backward launches)', 'bound': 'fp32_fma', 'achieved': eq_tf,
+                                'peak': fp32_peak, 'peak_kind': f'148 SM x 128 FMA/clk x 2 x {sm_mhz:.0f} MHz', 'unit': 'TFLOP/s',
+                                'frac': eq_tf / fp32_peak, 'flop_per_step': nce_flops_step, 'share_of_step': nce_ms / K / prof_ms}
+        n_prop_layers = max(L, 2 * hp.get('high_order', 0))
+        emb_per_step = 2.0 * views * n_prop_layers * nnz if model_name != 'sgl' else 2.0 * L * nnz * (1 + 2 * hp['keep_rate'])
 
-    # ---- CPU baseline on this box's host cores (bounded sample) ----
-    cpu = None
-    # rank 0, N = 1 only (the N > 1 lines of the scaling series carry null); models oracle.CpuTrainer can step
-    if world == 1 and not args.no_cpu_baseline and model_name in ('lightgcn', 'simgcl', 'sgl', 'directau'):
-        times, threads = cpu_steps(model_name, hp, rows, cols, n_user, n_item, [b.numpy() for b in host_batches[:3]],
-                                   budget_s=45.0, max_steps=2, warmup=1)
-        cpu = {'value': 1.0 / float(np.median(times)), 'unit': 'steps/s', 'cores': threads, 'kind': 'port',
-               'sample': f'{len(times)} full training steps after 1 warm-up (same graph, batch, hyper-parameters); oracle port of the reference CPU path'}
+        # ---- CPU baseline on this box's host cores (bounded sample) ----
+        cpu = None
+        # rank 0, N = 1 only (the N > 1 lines of the scaling series carry null)
+        if world == 1 and not args.no_cpu_baseline and not graph.startswith('synthetic-xl'):
+            try:
+                line = cpu_baseline_subprocess(args.workload, 2, 45.0)
+                cpu = dict(line.get('cpu_baseline') or {'error': line.get('unavailable')})
+                if line.get('cpu_baseline') and hp.get('keep_rate', 1.0) == 1.0:
+                    # "tuned CPU": the same step with the adjacency in CSR, so the GPU ratio is not flattered by the COO layout
+                    try:
+                        t2 = cpu_baseline_subprocess(args.workload, 1, 30.0, csr=True)['cpu_baseline']
+                        cpu['tuned_csr'] = {'value': t2['value'], 'unit': 'steps/s', 'cores': t2['cores'], 'sample': t2['sample']}
+                    except Exception as e:      # noqa: BLE001 -- a baseline extra must never cost the bench line
+                        cpu['tuned_csr'] = {'error': repr(e)[:300]}
+            except Exception as e:      # noqa: BLE001
+                cpu = {'error': repr(e)[:300]}
 
-        try:        # "tuned CPU": the same step with the adjacency in CSR, so the GPU ratio is not flattered by the COO layout
-            t2, _ = cpu_steps(model_name, hp, rows, cols, n_user, n_item, [b.numpy() for b in host_batches[:3]], budget_s=30.0,
-                              max_steps=1, warmup=1, csr=True, threads=threads)
-            cpu['tuned_csr'] = {'value': 1.0 / float(np.median(t2)), 'unit': 'steps/s', 'cores': threads,
-                                'sample': f'{len(t2)} step after 1 warm-up, adjacency as torch sparse CSR (one-line change of the reference)'}
-        except Exception as e:      # noqa: BLE001 -- a baseline extra must never cost the bench line
-            cpu['tuned_csr'] = {'error': repr(e)}
+        value = units * 1e3 / ms_res
+        out = {
+            'metric': 'train_steps_per_sec', 'value': value, 'unit': 'steps/s', 'n_gpus': world, 'steps': K, 'warmup': W,
+            'ms_per_step': ms_res, 'higher_is_better': True, 'scaling': scaling_label(args.parallel, args.workload, n_user, n_item, world), 'vs_baseline': None, 'dtype': 'f32',
+            'data': 'synthetic', 'config': workload_config(args.workload, n_user, n_item, len(rows), world, mode),
+            'batches_per_sync_step': units, 'optimizer_steps_per_sec': 1e3 / ms_res,
+            'e2e': {'value': units * 1e3 / ms_e2e, 'unit': 'steps/s', 'ms_per_step': ms_e2e, 'h2d_bytes_per_step': 3 * BATCH * 8,
+                    'd2h_bytes_per_step': 4 * (1 + {'simgcl': 3, 'sgl': 3, 'lightgcn': 2}.get(model_name, 3)),
+                    'how': 'sslrec_b200.trainer.Trainer.train_epoch loop: pinned-host batch -> H2D, cal_loss, backward, FusedAdam.step, '
+                           'loss + loss terms copied D2H asynchronously and read one step later (all reads drained inside the timed region)'},
+            'e2e_strict_sync': {'value': units * 1e3 / ms_e2e_strict, 'unit': 'steps/s', 'ms_per_step': ms_e2e_strict,
+                                'how': 'the reference trainer\'s blocking reads: loss.item() after cal_loss and float(v) per loss term (trainer.py:66,72)'},
+            'e2e_epoch': epoch,
+            'gpu_launches': launches, 'gpu_launches_per_step': launches / K,
+            'embeddings_propagated_per_sec': emb_per_step * value,
+            'roofline': roofline, 'roofline_infonce': roofline_nce, 'cpu_baseline': cpu, 'row_shard': None,
+            'roofline_note': 'roofline = the SpMM BASELINE.json names (HBM-bound); roofline_infonce = the kernel with the largest share of this '
+                             'step (tensor-bound contraction); both carry share_of_step',
+            'clocks': clocks, 'clocks_e2e': clocks_e2e, 'kernel_ms_per_step': {k: v['ms'] / K for k, v in summ.items()}, 'profiled_ms_per_step': prof_ms,
+            'timing_log': timing_log, 'host': {'cpu_count': os.cpu_count(), 'affinity': len(os.sched_getaffinity(0)), 'loadavg': os.getloadavg(),
+                                                  'usable_cpus': usable_cpus()},
+        }
+        return out
 
-    value = units * 1e3 / ms_res
-    out = {
-        'metric': 'train_steps_per_sec', 'value': value, 'unit': 'steps/s', 'n_gpus': world, 'steps': K, 'warmup': W,
-        'ms_per_step': ms_res, 'higher_is_better': True, 'scaling': scaling_label(args.parallel, args.workload, n_user, n_item, world), 'vs_baseline': None, 'dtype': 'f32',
-        'data': 'synthetic', 'config': workload_config(args.workload, n_user, n_item, len(rows), world, mode),
-        'batches_per_sync_step': units, 'optimizer_steps_per_sec': 1e3 / ms_res,
-        'e2e': {'value': units * 1e3 / ms_e2e, 'unit': 'steps/s', 'ms_per_step': ms_e2e, 'h2d_bytes_per_step': 3 * BATCH * 8,
-                'd2h_bytes_per_step': 4 * (1 + {'simgcl': 3, 'sgl': 3, 'lightgcn': 2}.get(model_name, 3)),
-                'how': 'sslrec_b200.trainer.Trainer.train_epoch loop: pinned-host batch -> H2D, cal_loss, backward, FusedAdam.step, '
-                       'loss + loss terms copied D2H asynchronously and read one step later (all reads drained inside the timed region)'},
-        'e2e_strict_sync': {'value': units * 1e3 / ms_e2e_strict, 'unit': 'steps/s', 'ms_per_step': ms_e2e_strict,
-                            'how': 'the reference trainer\'s blocking reads: loss.item() after cal_loss and float(v) per loss term (trainer.py:66,72)'},
-        'e2e_epoch': epoch,
-        'gpu_launches': launches, 'gpu_launches_per_step': launches / K,
-        'embeddings_propagated_per_sec': emb_per_step * value,
-        'roofline': roofline, 'roofline_infonce': roofline_nce, 'cpu_baseline': cpu,
-        'roofline_note': 'roofline = the SpMM BASELINE.json names (HBM-bound); roofline_infonce = the kernel with the largest share of this '
-                         'step (tensor-bound contraction); both carry share_of_step',
-        'clocks': clocks, 'clocks_e2e': clocks_e2e, 'kernel_ms_per_step': {k: v['ms'] / K for k, v in summ.items()}, 'profiled_ms_per_step': prof_ms,
-        'timing_log': timing_log, 'host': {'cpu_count': os.cpu_count(), 'affinity': len(os.sched_getaffinity(0)), 'loadavg': os.getloadavg(),
-                                              'usable_cpus': usable_cpus()},
-    }
-    print(json.dumps(out))
+    out = assemble() if rank == 0 else None
+    torch.cuda.synchronize()
+
+    # ---- north_star's partition next to the data-parallel headline: the row-sharded LightGCN step on the config-4 graph
+    # family scaled to N/8 (bench_rowshard.py), on every --gpus N line of the default workload ----
+    row_shard = None
+    want_leg = args.row_shard == 'on' or (args.row_shard == 'auto' and args.workload == 'simgcl-amazon')
+    if want_leg:
+        del model, opt, params, dev_batches, host_batches
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
+        def fallback():
+            if rank != 0:
+                return None
+            out['row_shard'] = {'error': f'abandoned after {args.row_shard_deadline:.0f} s (a rank wedged inside the leg)'}
+            return json.dumps(out)
+        dog = Watchdog(args.row_shard_deadline, fallback)
+        try:
+            import bench_rowshard
+            row_shard = bench_rowshard.leg(dist, rank, world, dev, steps=5, warmup=2,
+                                           log=(lambda m: print('[row_shard] ' + m, file=sys.stderr, flush=True)) if rank == 0 else (lambda m: None))
+        except Exception as e:      # noqa: BLE001 -- the leg is an extra record; it must never cost the bench line
+            row_shard = {'error': repr(e)[:500]}
+            if world > 1:
+                print(f'[row_shard] rank {rank}: {e!r}', file=sys.stderr, flush=True)
+    else:
+        dog = None
+
+    if rank == 0:
+        out['row_shard'] = row_shard
+        print(json.dumps(out), flush=True)
+    if dog is not None:
+        dog.cancel()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def run_xl(args):
+    """BASELINE.json configs[3]: LightGCN on the synthetic 10 M x 2 M / 300 M-edge graph, d = 128, row-sharded over the
+    GPUs (strong scaling: the same graph at every N).  The bench line's value is the sharded step; rank 0's single-GPU run
+    of the same graph is measured in the same process when N > 1 (``row_shard.baselines``)."""
+    rank, local_rank, world = rank_world()
+    import bench_rowshard as R
+    import sslrec_b200  # noqa: F401
+    from sslrec_b200 import _lib
+    torch.cuda.set_device(local_rank)
+    torch.set_num_threads(min(4, torch.get_num_threads()))
+    dev = torch.device('cuda', local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=dev)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    l0 = _lib.launch_count()
+    rec = R.leg(dist, rank, world, dev, steps=args.steps, warmup=max(args.warmup, 3), full=True, baselines=True,
+                log=(lambda m: print('[xl] ' + m, file=sys.stderr, flush=True)) if rank == 0 else (lambda m: None))
+    launches = _lib.launch_count() - l0
+    if rank == 0:
+        if sampler is not None:
+            sampler.sample()
+        peaks, peak_kind = measured_peaks()
+        one = rec if world > 1 else rec['baselines']['one_gpu_config4']
+        ms, spmm_ms, n_launch = one['ms_per_step'], one['spmm_ms'], max(1.0, one.get('spmm_launches', 2 * R.LAYERS))
+        n_user, n_item, n_edge = R.EIGHTH[0] * 8, R.EIGHTH[1] * 8, R.EIGHTH[2] * 8
+        nnz_rank = one.get('nnz_per_rank', one.get('nnz'))
+        rows_rank = one.get('rows_per_rank', n_user + n_item)
+        row = 4 * R.DIM
+        alg = nnz_rank * (8 + row) + rows_rank * (16 + 2 * row)           # gathers + (col, val) + work item + one row read + one written
+        achieved = alg / (spmm_ms / n_launch * 1e-3) / 1e9
+        out = {
+            'metric': 'train_steps_per_sec', 'value': 1e3 / ms, 'unit': 'steps/s', 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
+            'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': 'lightgcn training step on the synthetic config-4 graph (BASELINE.json configs[3])', 'model_name': 'lightgcn', 'graph': 'synthetic-xl',
+                       'n_user': n_user, 'n_item': n_item, 'nnz': 2 * n_edge, 'batch': BATCH, 'global_batch': BATCH, 'dim': R.DIM, 'layers': R.LAYERS,
+                       'parallelism': ('single GPU' if world == 1 else f'x{world}: rows of A and E sharded, all-gather of every layer output fused into the SpMM epilogue (NVLink peer stores)'),
+                       'l2': 'no explicit flush: the 6.1 GB tables exceed the 126 MB L2 by 50x'},
+            'e2e': {'value': 1e3 / one['e2e_ms_per_step'], 'unit': 'steps/s', 'ms_per_step': one['e2e_ms_per_step'], 'h2d_bytes_per_step': 3 * BATCH * 8, 'd2h_bytes_per_step': 4,
+                    'how': 'batch from pinned host memory -> H2D, cal_loss, backward, (sharded) FusedAdam.step, loss.item() every step'},
+            'gpu_launches': launches,
+            'embeddings_propagated_per_sec': 2.0 * R.LAYERS * 2 * n_edge * 1e3 / ms,
+            'roofline': {'kernel': 'prop_kernel (per rank, all forward + transposed-backward launches)', 'bound': 'hbm', 'achieved': achieved, 'peak': peaks['hbm_gbs'],
+                         'peak_kind': peak_kind + ' (burst copy)', 'unit': 'GB/s', 'frac': achieved / peaks['hbm_gbs'], 'traffic': ncu_traffic('prop_kernel', 'views1_dim128_synthetic-xl'),
+                         'avg_launch_ms': spmm_ms / n_launch, 'alg_bytes_per_launch': alg, 'share_of_step': spmm_ms / ms,
+                         'note': 'algorithmic bytes count every gathered row once per stored entry (the table is 50x the L2)'},
+            'cpu_baseline': None, 'row_shard': rec, 'clocks': sampler.result() if sampler is not None else None,
+        }
+        print(json.dumps(out), flush=True)
     if dist is not None:
         dist.destroy_process_group()
 
@@ -566,6 +719,11 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='simgcl-amazon', choices=sorted(WORKLOADS))
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--cpu-budget', type=float, default=170.0, help='--impl reference: wall-clock budget of the timed CPU steps (s)')
+    ap.add_argument('--cpu-csr', action='store_true', help='--impl reference: adjacency converted with to_sparse_csr() ("tuned CPU")')
+    ap.add_argument('--row-shard', default='auto', choices=['auto', 'on', 'off'],
+                    help="attach the row-sharded config-4-family record ('auto': on the default workload only)")
+    ap.add_argument('--row-shard-deadline', type=float, default=420.0, help='seconds after which a wedged row-shard leg is abandoned')
     ap.add_argument('--parallel', default='auto', choices=['auto', 'dp', 'shard'],
                     help='N > 1: dp = one batch per GPU + gradient all-reduce (weak scaling); shard = one batch, table rows sharded')
     args = ap.parse_args()
@@ -575,7 +733,10 @@ def main():
     else:
         if not torch.cuda.is_available():
             raise SystemExit('bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)')
-        run_ours(args)
+        if args.workload == 'lightgcn-xl':
+            run_xl(args)
+        else:
+            run_ours(args)
 
 
 if __name__ == '__main__':

@@ -44,11 +44,15 @@ extern "C" {
 #define SSL_MAX_VIEWS 4
 #define SSL_MAX_SUM_SRC 6
 #define SSL_MAX_DIM 128    /* embedding_size must be a multiple of 4 and <= 128 */
+#define SSL_MAX_PEERS 7    /* other GPUs of the node whose tables a kernel stores to over NVLink (8-GPU NVSwitch domain) */
 
 SSL_API int ssl_version(void);
 SSL_API const char *ssl_last_error(void);
 /* number of kernel launches issued by this library since load (bench.py's gpu_launches) */
 SSL_API int64_t ssl_launch_count(void);
+/* process-wide switches for tests and A/B profiling: "prop_interleaved" = 1 disables the view-major
+ * propagation variant (every view of a row is then accumulated by one thread) */
+SSL_API int ssl_set_option(const char *name, int64_t value);
 
 /* ------------------------------------------------------------------------------------------
  * a1/a2  adjacency plan -- replaces the torch sparse COO tensor built by
@@ -70,6 +74,13 @@ typedef struct ssl_plan ssl_plan;
 SSL_API int ssl_plan_create(ssl_plan **out, const int32_t *h_rowptr, const int32_t *d_colidx, const float *d_vals,
                     const int32_t *d_rev, int64_t n_rows, int64_t n_cols, int64_t nnz, int64_t row_offset,
                     int64_t side_split, void *stream);
+/* Row-sharded multi-GPU: the plan owns the global rows [a0, a1) followed by [b0, b1) -- a GPU's share
+ * of the user rows and of the item rows, so every GPU gets the same mix of both sides; h_rowptr runs over the
+ * n_rows = (a1-a0) + (b1-b0) local rows in that order, column ids stay global.  ssl_plan_create is the single-range
+ * case [row_offset, row_offset + n_rows). */
+SSL_API int ssl_plan_create_ranges(ssl_plan **out, const int32_t *h_rowptr, const int32_t *d_colidx, const float *d_vals,
+                           const int32_t *d_rev, int64_t n_rows, int64_t n_cols, int64_t nnz, int64_t a0, int64_t a1,
+                           int64_t b0, int64_t b1, int64_t side_split, void *stream);
 SSL_API int ssl_plan_destroy(ssl_plan *plan);
 /* work-list statistics: out[0]=items, out[1]=split rows, out[2]=segments, out[3]=max row nnz */
 SSL_API int ssl_plan_stats(const ssl_plan *plan, int64_t out[4]);
@@ -91,16 +102,24 @@ SSL_API int ssl_plan_stats(const ssl_plan *plan, int64_t out[4]);
  * (dX = A_v^T dY evaluated on the same CSR with the mask key swapped).
  *
  * Layouts: x_in [n_cols, in_views, dim] (in_views = 1: all views read the same rows, or
- * = n_views); x_out, residual [n_rows, n_views, dim]; sum_src[i] [n_rows, sum_src_views[i], dim]
- * with sum_src_views[i] in {1, n_views}; sum_out [n_rows, n_views, dim] or [n_rows, dim].
- * Row-wise pointers are indexed by LOCAL row (0..n_rows), x_in by global column id.
+ * = n_views); x_out, residual [n_cols, n_views, dim]; sum_src[i] [n_cols, sum_src_views[i], dim]
+ * with sum_src_views[i] in {1, n_views}; sum_out [n_cols, n_views, dim] or [n_cols, dim].
+ * Every table is FULL height (n_cols = N rows) and addressed by the GLOBAL row id; a row-sharded
+ * plan reads and writes only the rows it owns.
+ *
+ * Fused all-gather (row-sharded multi-GPU, one NVSwitch domain): with n_peers > 0 every finished
+ * row of x_out / sum_out is also stored to the same row of x_out_peers[q] / sum_out_peers[q] --
+ * the other GPUs' tables, mapped into this process (CUDA IPC / symmetric memory) -- so after the
+ * launches of all ranks have completed (cross-GPU barrier, caller's job) every GPU holds the
+ * whole layer output; the NVLink stores overlap the gathers of the rows still being computed.
+ * This replaces "one NCCL allgather of the d-wide layer output per layer".
  *
  * edge_mode[v]: 0 keep all; 1 counter-based RNG: keep iff U(seed[v], edge_stream_id, row, col) >= 1-keep
  *               (floor(U + keep), aug_utils.py:28); 2 injected: edge_mask[v][p] != 0, p = CSR
  *               position (rev[p] when transpose).  edge_scale[v] multiplies kept values
  *               (1, or 1/keep for EdgeDrop(resize_val=True), hccf.py:33).
  * noise_mode[v]: 0 none; 1 RNG uniform(seed[v], noise_stream_id, row, elem);
- *               2 injected: noise_u[v] is a [n_rows, dim] U[0,1) tensor.
+ *               2 injected: noise_u[v] is a [n_cols, dim] U[0,1) tensor (global row).
  * ------------------------------------------------------------------------------------------ */
 typedef struct ssl_prop_args {
     int32_t dim, n_views, in_views, transpose;
@@ -125,6 +144,9 @@ typedef struct ssl_prop_args {
     uint32_t edge_stream_id;          /* RNG sub-stream of the edge mask: constant over the layers of one forward
                                          (lightgcn.py:36-37, sgl.py:27-28) or the layer index (hccf.py:47) */
     uint32_t noise_stream_id;         /* RNG sub-stream of the perturbation: the layer index (simgcl.py:26-27) */
+    int32_t n_peers;                  /* 0 on one GPU */
+    float *x_out_peers[SSL_MAX_PEERS];    /* peers' copies of the x_out table (same shape, same row addressing) */
+    float *sum_out_peers[SSL_MAX_PEERS];  /* peers' copies of the sum_out table */
 } ssl_prop_args;
 
 SSL_API int ssl_propagate_layer(const ssl_plan *plan, const ssl_prop_args *args, void *stream);
@@ -232,6 +254,11 @@ SSL_API int ssl_axpy(const float *x, float *y, int64_t n, const float *gscale, f
  * ------------------------------------------------------------------------------------------ */
 SSL_API int ssl_adam_step(float *p, const float *g, float *m, float *v, int64_t n, int64_t step, double lr, double beta1,
                   double beta2, double eps, double weight_decay, void *stream);
+/* Row-sharded Adam: the same update on the n elements p[0..n) this GPU owns (p, g, m, v already point at the owned
+ * range), with every new parameter value also stored to the same position of p_peers[q] (the other GPUs' replicas of
+ * the table, mapped over NVLink) -- the all-gather of the updated table fused into the optimizer kernel. */
+SSL_API int ssl_adam_step_peers(float *p, float *const *p_peers, int32_t n_peers, const float *g, float *m, float *v, int64_t n,
+                        int64_t step, double lr, double beta1, double beta2, double eps, double weight_decay, void *stream);
 
 /* ------------------------------------------------------------------------------------------
  * a18  full_predict + _mask_predict (lightgcn.py:58-66, base_model.py:35-36) and the top-k that

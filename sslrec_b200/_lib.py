@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, 'lib', 'libsslrec_b200.so')
 MAX_VIEWS = 4
 MAX_SUM_SRC = 6
 MAX_DIM = 128
+MAX_PEERS = 7
 
 c_f32p = C.POINTER(C.c_float)
 c_i32p = C.POINTER(C.c_int32)
@@ -35,6 +36,7 @@ class PropArgs(C.Structure):
         ('noise_mode', C.c_int32 * MAX_VIEWS), ('noise_u', vp * MAX_VIEWS),
         ('noise_eps', C.c_float), ('seed', C.c_uint64 * MAX_VIEWS),
         ('edge_stream_id', C.c_uint32), ('noise_stream_id', C.c_uint32),
+        ('n_peers', C.c_int32), ('x_out_peers', vp * MAX_PEERS), ('sum_out_peers', vp * MAX_PEERS),
     ]
 
 
@@ -54,6 +56,8 @@ def _load():
         'ssl_last_error': (C.c_char_p, []),
         'ssl_launch_count': (i64, []),
         'ssl_plan_create': (C.c_int, [C.POINTER(vp), vp, vp, vp, vp, i64, i64, i64, i64, i64, vp]),
+        'ssl_plan_create_ranges': (C.c_int, [C.POINTER(vp), vp, vp, vp, vp, i64, i64, i64, i64, i64, i64, i64, i64, vp]),
+        'ssl_set_option': (C.c_int, [C.c_char_p, i64]),
         'ssl_plan_destroy': (C.c_int, [vp]),
         'ssl_plan_stats': (C.c_int, [vp, c_i64p]),
         'ssl_propagate_layer': (C.c_int, [vp, C.POINTER(PropArgs), vp]),
@@ -72,6 +76,7 @@ def _load():
         'ssl_sum': (C.c_int, [vp, i64, f32, vp, vp]),
         'ssl_axpy': (C.c_int, [vp, vp, i64, vp, f32, vp]),
         'ssl_adam_step': (C.c_int, [vp, vp, vp, vp, i64, i64, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, vp]),
+        'ssl_adam_step_peers': (C.c_int, [vp, C.POINTER(vp), i32, vp, vp, vp, i64, i64, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, vp]),
         'ssl_predict_mask': (C.c_int, [vp, i64, vp, i64, vp, i64, i64, i32, vp, vp, vp, vp, vp]),
         'ssl_topk': (C.c_int, [vp, i64, i64, i32, vp, vp, vp]),
         'ssl_align_fwd': (C.c_int, [vp, vp, i64, i32, vp, vp]),

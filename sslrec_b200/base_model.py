@@ -35,7 +35,11 @@ class BaseModel(nn.Module):
         """``user_embeds`` / ``item_embeds`` (the checkpoint contract) as adjacent
         views of ONE [N, d] storage, xavier-uniform per side in the reference's order
         (lightgcn.py:21-22) so the same torch seed gives the same initial weights."""
-        table = torch.empty(self.user_num + self.item_num, self.embedding_size)
+        # optional key model.init_on_device: draw the initial weights with the device generator (a 6 GB table -- BASELINE
+        # config 4 -- takes tens of seconds and 6 GB of host memory per process on the CPU generator); same distribution,
+        # different bits than the reference's CPU draw
+        on_dev = configs['model'].get('init_on_device', False) and str(configs.get('device', 'cpu')).startswith('cuda')
+        table = torch.empty(self.user_num + self.item_num, self.embedding_size, device=configs['device'] if on_dev else None)
         nn.init.xavier_uniform_(table[:self.user_num])
         nn.init.xavier_uniform_(table[self.user_num:])
         self.user_embeds = nn.Parameter(table[:self.user_num])
@@ -66,20 +70,55 @@ class BaseModel(nn.Module):
         self._state = None
         self._inject = None        # tests: dict of injected masks / noise
         self.comm = None           # parallel.RowShard for row-sharded multi-GPU runs
+        # optional: data_handler.plan_source(device, row_ranges, side_split) -> GraphPlan builds the CSR plan without a
+        # torch sparse COO tensor (BASELINE config 4: 600 M stored entries are generated and sorted on the device)
+        self._plan_source = getattr(data_handler, 'plan_source', None)
 
     def _plan(self, adj=None) -> GraphPlan:
         """CSR plan of an adjacency tensor, built once per (tensor, device)."""
         adj = self.adj if adj is None else adj
         dev = self.user_embeds.device
-        key = (id(adj), str(dev))
+        sharded = self.comm is not None and self.comm.shard_propagation
+        need_rev = self._inject is not None
+        # keyed by the tensor's storage (an id() can be reused after the tensor is freed; the entry also holds a reference)
+        key = (None if adj is None else (adj._values().data_ptr(), adj._nnz()), str(dev), sharded, need_rev)
         if key not in self._plans:
             if dev.type != 'cuda':
                 raise RuntimeError('sslrec_b200 models run on CUDA only (move the model with .to("cuda")); there is no CPU path')
-            if self.comm is not None and self.comm.shard_propagation:
-                self._plans[key] = self.comm.make_plan(adj, dev, side_split=self.user_num)
+            if adj is None:
+                if self._plan_source is None:
+                    raise RuntimeError('the data handler provides neither torch_adj nor plan_source')
+                plan = self._plan_source(dev, self.comm.ranges if sharded else None, self.user_num)
+            elif sharded:
+                plan = self.comm.make_plan(adj, dev, side_split=self.user_num)
             else:
-                self._plans[key] = GraphPlan.from_torch_adj(adj, dev, need_rev=self._inject is not None, side_split=self.user_num)
-        return self._plans[key]
+                plan = GraphPlan.from_torch_adj(adj, dev, need_rev=need_rev, side_split=self.user_num)
+            self._plans[key] = (plan, adj)
+        return self._plans[key][0]
+
+    def shard_to(self, comm) -> None:
+        """Attach a parallel.RowShard.  When it row-shards the propagation, the flat [N, d] parameter table moves into a
+        shared table (every rank maps every peer's replica) so the sharded Adam can store the rows it updates straight
+        into the peers' replicas; rank 0's values are broadcast so all replicas start identical."""
+        self.comm = comm
+        self._plans.clear()
+        if comm is None or not comm.shard_propagation:
+            return
+        dev = self.user_embeds.device
+        tb = comm.table('params', (self.user_num + self.item_num, self.embedding_size), dev)
+        with torch.no_grad():
+            tb.t[:self.user_num].copy_(self.user_embeds.data)
+            tb.t[self.user_num:].copy_(self.item_embeds.data)
+            comm.dist.broadcast(tb.t, src=0)
+        self.user_embeds.data = tb.t[:self.user_num]
+        self.item_embeds.data = tb.t[self.user_num:]
+        comm.barrier()
+        # what the sharded optimizer needs per parameter: the owned row range and the peers' base addresses of that parameter
+        row_bytes = 4 * self.embedding_size
+        self.row_shards = {
+            id(self.user_embeds): (comm.u0, comm.u1, [p for p in tb.peer_ptrs]),
+            id(self.item_embeds): (comm.i0 - self.user_num, comm.i1 - self.user_num, [p + self.user_num * row_bytes for p in tb.peer_ptrs]),
+        }
 
     def _train_csr(self, device):
         """Training interactions as a device CSR (int32), built once: the mask of ``_mask_predict`` without the

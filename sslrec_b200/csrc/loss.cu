@@ -339,8 +339,12 @@ __device__ __forceinline__ void adam1(float &p, float g, float &m, float &v, con
     const float denom = sqrtf(v) * inv_bc2_sqrt + eps;
     p -= step_size * (m / denom);
 }
+struct PeerPtrs {
+    float *p[SSL_MAX_PEERS];
+    int n;
+};
 __global__ void adam_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m, float *__restrict__ v,
-                            int64_t n, AdamK k) {
+                            int64_t n, AdamK k, PeerPtrs peers) {
     const int64_t n4 = n / 4;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
         float4 pv = *reinterpret_cast<float4 *>(p + i * 4), mv = *reinterpret_cast<float4 *>(m + i * 4),
@@ -351,12 +355,14 @@ __global__ void adam_kernel(float *__restrict__ p, const float *__restrict__ g, 
         adam1(pv.z, gv.z, mv.z, vv.z, k);
         adam1(pv.w, gv.w, mv.w, vv.w, k);
         *reinterpret_cast<float4 *>(p + i * 4) = pv;
+        for (int q = 0; q < peers.n; ++q) *reinterpret_cast<float4 *>(peers.p[q] + i * 4) = pv;   // NVLink stores
         *reinterpret_cast<float4 *>(m + i * 4) = mv;
         *reinterpret_cast<float4 *>(v + i * 4) = vv;
     }
     if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
         const int64_t i = n4 * 4 + threadIdx.x;
         adam1(p[i], g[i], m[i], v[i], k);
+        for (int q = 0; q < peers.n; ++q) peers.p[q][i] = p[i];
     }
 }
 
@@ -531,11 +537,18 @@ extern "C" int ssl_axpy(const float *x, float *y, int64_t n, const float *gscale
     return SSL_OK;
 }
 
-extern "C" int ssl_adam_step(float *p, const float *g, float *m, float *v, int64_t n, int64_t step, double lr, double beta1,
-                             double beta2, double eps, double weight_decay, void *stream) {
+extern "C" int ssl_adam_step_peers(float *p, float *const *p_peers, int32_t n_peers, const float *g, float *m, float *v, int64_t n,
+                                   int64_t step, double lr, double beta1, double beta2, double eps, double weight_decay, void *stream) {
     SSL_CHECK_ARG(p && g && m && v && step >= 1, "ssl_adam_step: bad argument");
     SSL_CHECK_ARG(((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v)) & 15) == 0,
                   "ssl_adam_step: pointers must be 16-byte aligned");
+    SSL_CHECK_ARG(n_peers >= 0 && n_peers <= SSL_MAX_PEERS && (n_peers == 0 || p_peers != nullptr), "ssl_adam_step_peers: bad peer list");
+    PeerPtrs peers{};
+    peers.n = n_peers;
+    for (int q = 0; q < n_peers; ++q) {
+        SSL_CHECK_ARG(p_peers[q] != nullptr && (reinterpret_cast<uintptr_t>(p_peers[q]) & 15) == 0, "ssl_adam_step_peers: peer pointer %d null or unaligned", q);
+        peers.p[q] = p_peers[q];
+    }
     if (n == 0) return SSL_OK;
     const double bc1 = 1.0 - std::pow(beta1, (double)step);
     const double bc2 = 1.0 - std::pow(beta2, (double)step);
@@ -543,9 +556,14 @@ extern "C" int ssl_adam_step(float *p, const float *g, float *m, float *v, int64
     const float inv_bc2_sqrt = (float)(1.0 / std::sqrt(bc2));
     const int blocks = (int)std::min<int64_t>(ssl::kNumSM * 8, (n / 4 + 255) / 256 + 1);
     const AdamK k{(float)beta1, (float)beta2, (float)(1.0 - beta1), (float)(1.0 - beta2), step_size, inv_bc2_sqrt, (float)eps, (float)weight_decay};
-    adam_kernel<<<blocks, 256, 0, STREAM>>>(p, g, m, v, n, k);
+    adam_kernel<<<blocks, 256, 0, STREAM>>>(p, g, m, v, n, k, peers);
     SSL_LAUNCH_CHECK("adam_kernel");
     return SSL_OK;
+}
+
+extern "C" int ssl_adam_step(float *p, const float *g, float *m, float *v, int64_t n, int64_t step, double lr, double beta1,
+                             double beta2, double eps, double weight_decay, void *stream) {
+    return ssl_adam_step_peers(p, nullptr, 0, g, m, v, n, step, lr, beta1, beta2, eps, weight_decay, stream);
 }
 
 extern "C" int ssl_predict_mask(const float *users_tab, int64_t u_stride, const float *items_tab, int64_t i_stride,

@@ -11,14 +11,27 @@
 // first.  Long rows are split into segments whose partial sums go to a plan-owned scratch; the
 // last segment to finish (atomic ticket) adds the partials in segment order -- the summation
 // order of every output element is fixed, so results are bit-reproducible run to run.
+//
+// Row-sharded multi-GPU: a plan may own two global row ranges (its share of the user
+// rows and of the item rows); every per-row pointer is a FULL [N, ...] table addressed by the global
+// row.  The epilogue stores a finished row to this GPU's table and to the same row of every peer's
+// table (pointers into the peers' HBM mapped over NVLink: x_out_peers / sum_out_peers), so the
+// all-gather of the layer output is fused into the SpMM and its NVLink traffic overlaps the gathers.
+//
+// View-major variant (VM): with per-view inputs the grid's y dimension is the view and a thread
+// keeps one accumulator.  CTAs are scheduled x-fastest, so all rows of view 0 run before view 1:
+// the gathered working set is one view's rows (41 MB at the amazon shape) instead of the interleaved
+// [N, V, d] table (123 MB, which thrashed the 126 MB L2 at 57 % hits).
 #include <algorithm>
 #include <cmath>
+#include <string>
 #include <vector>
 
 #include "common.cuh"
 
 struct ssl_plan {
     int64_t n_rows, n_cols, nnz, row_offset;
+    int64_t split_local, off_a, off_b;   // global row = local + (local < split_local ? off_a : off_b)
     const int32_t *colidx;
     const float *vals;
     const int32_t *rev;
@@ -34,6 +47,7 @@ namespace {
 constexpr int kMinSeg = 128;       // rows up to this many entries are never split
 constexpr int kThreads = 256;
 constexpr int kPartialStride = SSL_MAX_VIEWS * SSL_MAX_DIM;
+bool g_force_interleaved = false;   // tests / A-B profiling: ssl_set_option("prop_interleaved", 1)
 
 struct PlanDev {
     const int32_t *colidx;
@@ -43,8 +57,9 @@ struct PlanDev {
     const int2 *long_info;
     int32_t *counters;
     float *partial;
-    int64_t n_items;
-    uint32_t row_offset;
+    int64_t n_items, n_long;
+    int32_t split_local;
+    uint32_t off_a, off_b;
 };
 
 __device__ __forceinline__ float sgnf(float x) { return (x > 0.f) ? 1.f : ((x < 0.f) ? -1.f : 0.f); }
@@ -52,13 +67,15 @@ __device__ __forceinline__ float sgnf(float x) { return (x > 0.f) ? 1.f : ((x < 
 // MODE 0: all views read the same input row and no view masks edges -> one accumulator, perturbed per view in the
 //         epilogue (SimGCL layer 1);  MODE 1: per-view inputs, no edge masks -> V accumulators, ONE weight per entry;
 // MODE 2: per-view edge masks -> V accumulators, V weights per entry.
-template <int G, int V, int MODE>
+// VM (view-major): V is 1 here, the thread serves view blockIdx.y of a.n_views; MODE 1 / 2 only.
+template <int G, int V, int MODE, bool VM>
 __global__ void __launch_bounds__(kThreads, (V <= 3) ? 4 : 3) prop_kernel(PlanDev p, ssl_prop_args a) {
     constexpr int RPW = 32 / G;
     constexpr bool SHARED = MODE == 0;
     constexpr int NA = SHARED ? 1 : V;
     constexpr int NW = (MODE == 2) ? V : 1;        // distinct weights per entry
     constexpr int UNR = (NA == 1 && G >= 8) ? 8 : 4;   // entries whose row gathers are in flight together (single-view: 8)
+    static_assert(!VM || (V == 1 && MODE != 0), "view-major serves one view per thread");
     const int lane = threadIdx.x & 31;
     const int gl = lane % G;
     const int grp = lane / G;
@@ -68,17 +85,20 @@ __global__ void __launch_bounds__(kThreads, (V <= 3) ? 4 : 3) prop_kernel(PlanDe
     const int dim = a.dim;
     const int col = gl * 4;
     const bool lane_on = col < dim;
+    const int vbase = VM ? (int)blockIdx.y : 0;    // first (only) view of this thread
+    const int nv = VM ? a.n_views : V;             // views interleaved in the row-wise tables
 
     int4 it = make_int4(-1, 0, 0, -1);
     if (item_idx < p.n_items) it = p.items[item_idx];
     const int r = it.x;
-    const uint32_t grow = p.row_offset + (uint32_t)r;
+    const uint32_t grow = (uint32_t)r + ((r < p.split_local) ? p.off_a : p.off_b);    // global row
 
     float4 acc[NA];
 #pragma unroll
     for (int v = 0; v < NA; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
 
     const size_t in_row = (size_t)a.in_views * dim;
+    const float *xin = a.x_in + ((VM && a.in_views != 1) ? vbase * dim : 0);
     for (int base = it.y; base < it.z; base += G) {
         const int pe = base + gl;
         const bool valid = pe < it.z;
@@ -89,14 +109,14 @@ __global__ void __launch_bounds__(kThreads, (V <= 3) ? 4 : 3) prop_kernel(PlanDe
         for (int v = 0; v < NW; ++v) {
             float f = w;
             if (MODE == 2) {
-                const int mode = a.edge_mode[v];
+                const int mode = a.edge_mode[vbase + v];
                 if (mode == 1) {
                     const uint32_t kr = a.transpose ? (uint32_t)c : grow;
                     const uint32_t kc = a.transpose ? grow : (uint32_t)c;
-                    f = (valid && ssl::edge_keep_rng(a.seed[v], a.edge_stream_id, kr, kc, a.edge_keep[v])) ? w * a.edge_scale[v] : 0.f;
+                    f = (valid && ssl::edge_keep_rng(a.seed[vbase + v], a.edge_stream_id, kr, kc, a.edge_keep[vbase + v])) ? w * a.edge_scale[vbase + v] : 0.f;
                 } else if (mode == 2) {
                     const int q = valid ? (a.transpose ? __ldg(p.rev + pe) : pe) : 0;
-                    f = (valid && a.edge_mask[v][q]) ? w * a.edge_scale[v] : 0.f;
+                    f = (valid && a.edge_mask[vbase + v][q]) ? w * a.edge_scale[vbase + v] : 0.f;
                 }
             }
             wv[v] = f;
@@ -114,11 +134,11 @@ __global__ void __launch_bounds__(kThreads, (V <= 3) ? 4 : 3) prop_kernel(PlanDe
             }
 #pragma unroll
             for (int u = 0; u < UNR; ++u) {
-                const float *xr = a.x_in + (size_t)cj[u] * in_row + col;
+                const float *xr = xin + (size_t)cj[u] * in_row + col;
 #pragma unroll
                 for (int v = 0; v < NA; ++v) {
                     x[u][v] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (lane_on && wj[u][NW == 1 ? 0 : v] != 0.f) x[u][v] = ssl::ldg4(xr + ((a.in_views == 1) ? 0 : v * dim));
+                    if (lane_on && wj[u][NW == 1 ? 0 : v] != 0.f) x[u][v] = ssl::ldg4(xr + ((VM || a.in_views == 1) ? 0 : v * dim));
                 }
             }
 #pragma unroll
@@ -132,42 +152,46 @@ __global__ void __launch_bounds__(kThreads, (V <= 3) ? 4 : 3) prop_kernel(PlanDe
     // ---- split rows: publish the partial, the last arrival reduces in segment order ----
     if (it.w >= 0) {
         const int2 li = p.long_info[it.w];
-        float *mine = p.partial + (size_t)item_idx * kPartialStride;   // split items are items [0, n_slots)
+        // split items are items [0, n_slots); a slot holds every view's partial (view v at v * dim); a view-major launch
+        // keeps one arrival ticket per (view, long row)
+        int32_t *ticket = p.counters + (size_t)vbase * p.n_long + it.w;
+        float *mine = p.partial + (size_t)item_idx * kPartialStride + vbase * dim;
         if (lane_on) {
 #pragma unroll
             for (int v = 0; v < NA; ++v) *reinterpret_cast<float4 *>(mine + v * dim + col) = acc[v];
         }
         __threadfence();
         int last = 0;
-        if (gl == 0) last = (atomicAdd(p.counters + it.w, 1) == li.y - 1);
+        if (gl == 0) last = (atomicAdd(ticket, 1) == li.y - 1);
         last = __shfl_sync(gmask, last, 0, G);
         if (!last) return;
         __threadfence();
 #pragma unroll
         for (int v = 0; v < NA; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int s = 0; s < li.y; ++s) {
-            const float *ps = p.partial + (size_t)(li.x + s) * kPartialStride;
+            const float *ps = p.partial + (size_t)(li.x + s) * kPartialStride + vbase * dim;
             if (lane_on) {
 #pragma unroll
                 for (int v = 0; v < NA; ++v) ssl::add4(acc[v], __ldcg(reinterpret_cast<const float4 *>(ps + v * dim + col)));
             }
         }
-        if (gl == 0) p.counters[it.w] = 0;   // ready for the next launch (stream ordered)
+        if (gl == 0) *ticket = 0;   // ready for the next launch (stream ordered)
     }
 
-    // ---- epilogue: residual, perturbation, layer output, layer sum ----
+    // ---- epilogue: residual, perturbation, layer output (own table + peers' tables), layer sum ----
     float4 tot = make_float4(0.f, 0.f, 0.f, 0.f);
-    const size_t out_row = (size_t)r * V * dim;
+    const size_t out_row = (size_t)grow * nv * dim;
 #pragma unroll
-    for (int v = 0; v < V; ++v) {
-        float4 x = acc[SHARED ? 0 : v];
+    for (int vi = 0; vi < V; ++vi) {
+        const int v = vbase + vi;
+        float4 x = acc[SHARED ? 0 : vi];
         if (a.residual != nullptr && lane_on) ssl::add4(x, ssl::ldg4(a.residual + out_row + v * dim + col));
         const int nm = a.noise_mode[v];
         if (nm != 0) {
             float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
             if (lane_on) {
                 if (nm == 1) u = ssl::noise_u4_rng(a.seed[v], a.noise_stream_id, grow, (uint32_t)gl);
-                else u = ssl::ldg4(a.noise_u[v] + (size_t)r * dim + col);
+                else u = ssl::ldg4(a.noise_u[v] + (size_t)grow * dim + col);
             }
             float ss = u.x * u.x + u.y * u.y + u.z * u.z + u.w * u.w;
 #pragma unroll
@@ -179,44 +203,58 @@ __global__ void __launch_bounds__(kThreads, (V <= 3) ? 4 : 3) prop_kernel(PlanDe
             x.w += sgnf(x.w) * (u.w * sc);
         }
         if (!lane_on) continue;
-        if (a.x_out != nullptr) *reinterpret_cast<float4 *>(a.x_out + out_row + v * dim + col) = x;
+        const size_t o = out_row + v * dim + col;
+        if (a.x_out != nullptr) {
+            *reinterpret_cast<float4 *>(a.x_out + o) = x;
+            for (int q = 0; q < a.n_peers; ++q) *reinterpret_cast<float4 *>(a.x_out_peers[q] + o) = x;   // NVLink stores
+        }
         if (a.sum_out != nullptr) {
             for (int i = 0; i < a.n_sum_src; ++i) {
                 const int sv = a.sum_src_views[i];
-                ssl::add4(x, ssl::ldg4(a.sum_src[i] + ((size_t)r * sv + (sv == 1 ? 0 : v)) * dim + col));
+                ssl::add4(x, ssl::ldg4(a.sum_src[i] + ((size_t)grow * sv + (sv == 1 ? 0 : v)) * dim + col));
             }
             if (a.reduce_views) ssl::add4(tot, x);
-            else *reinterpret_cast<float4 *>(a.sum_out + out_row + v * dim + col) = x;
+            else {
+                *reinterpret_cast<float4 *>(a.sum_out + o) = x;
+                for (int q = 0; q < a.n_peers; ++q) *reinterpret_cast<float4 *>(a.sum_out_peers[q] + o) = x;
+            }
         }
     }
     if (a.sum_out != nullptr && a.reduce_views && lane_on) {
-        if (a.reg_src != nullptr) ssl::fma4(tot, a.reg_coef, ssl::ldg4(a.reg_src + (size_t)r * dim + col));
-        *reinterpret_cast<float4 *>(a.sum_out + (size_t)r * dim + col) = tot;
+        if (a.reg_src != nullptr) ssl::fma4(tot, a.reg_coef, ssl::ldg4(a.reg_src + (size_t)grow * dim + col));
+        const size_t o = (size_t)grow * dim + col;
+        *reinterpret_cast<float4 *>(a.sum_out + o) = tot;
+        for (int q = 0; q < a.n_peers; ++q) *reinterpret_cast<float4 *>(a.sum_out_peers[q] + o) = tot;
     }
 }
 
 template <int G, int V>
-int launch_gv(const ssl_plan *plan, const ssl_prop_args &a, int mode, cudaStream_t st) {
-    PlanDev p{plan->colidx, plan->vals, plan->rev, plan->items, plan->long_info, plan->counters,
-              plan->partial, plan->n_items, (uint32_t)plan->row_offset};
+int launch_gv(const ssl_plan *plan, const ssl_prop_args &a, int mode, bool view_major, cudaStream_t st) {
+    PlanDev p{plan->colidx, plan->vals, plan->rev, plan->items, plan->long_info, plan->counters, plan->partial,
+              plan->n_items, plan->n_long, (int32_t)plan->split_local, (uint32_t)plan->off_a, (uint32_t)plan->off_b};
     constexpr int RPW = 32 / G;
     const int64_t items_per_block = (int64_t)(kThreads / 32) * RPW;
     const int64_t grid = (plan->n_items + items_per_block - 1) / items_per_block;
     if (grid == 0) return SSL_OK;
-    if (mode == 0) prop_kernel<G, V, 0><<<(unsigned)grid, kThreads, 0, st>>>(p, a);
-    else if (mode == 1) prop_kernel<G, V, 1><<<(unsigned)grid, kThreads, 0, st>>>(p, a);
-    else prop_kernel<G, V, 2><<<(unsigned)grid, kThreads, 0, st>>>(p, a);
+    if (view_major) {
+        const dim3 g((unsigned)grid, (unsigned)a.n_views);
+        if (mode == 1) prop_kernel<G, 1, 1, true><<<g, kThreads, 0, st>>>(p, a);
+        else prop_kernel<G, 1, 2, true><<<g, kThreads, 0, st>>>(p, a);
+    } else if (mode == 0) prop_kernel<G, V, 0, false><<<(unsigned)grid, kThreads, 0, st>>>(p, a);
+    else if (mode == 1) prop_kernel<G, V, 1, false><<<(unsigned)grid, kThreads, 0, st>>>(p, a);
+    else prop_kernel<G, V, 2, false><<<(unsigned)grid, kThreads, 0, st>>>(p, a);
     SSL_LAUNCH_CHECK("prop_kernel");
     return SSL_OK;
 }
 
 template <int G>
-int launch_g(const ssl_plan *plan, const ssl_prop_args &a, int mode, cudaStream_t st) {
+int launch_g(const ssl_plan *plan, const ssl_prop_args &a, int mode, bool view_major, cudaStream_t st) {
+    if (view_major) return launch_gv<G, 1>(plan, a, mode, true, st);
     switch (a.n_views) {
-        case 1: return launch_gv<G, 1>(plan, a, mode, st);
-        case 2: return launch_gv<G, 2>(plan, a, mode, st);
-        case 3: return launch_gv<G, 3>(plan, a, mode, st);
-        case 4: return launch_gv<G, 4>(plan, a, mode, st);
+        case 1: return launch_gv<G, 1>(plan, a, mode, false, st);
+        case 2: return launch_gv<G, 2>(plan, a, mode, false, st);
+        case 3: return launch_gv<G, 3>(plan, a, mode, false, st);
+        case 4: return launch_gv<G, 4>(plan, a, mode, false, st);
     }
     return SSL_E_ARG;
 }
@@ -226,20 +264,32 @@ int launch_g(const ssl_plan *plan, const ssl_prop_args &a, int mode, cudaStream_
 extern "C" int ssl_plan_create(ssl_plan **out, const int32_t *h_rowptr, const int32_t *d_colidx, const float *d_vals,
                                const int32_t *d_rev, int64_t n_rows, int64_t n_cols, int64_t nnz, int64_t row_offset,
                                int64_t side_split, void *stream) {
+    return ssl_plan_create_ranges(out, h_rowptr, d_colidx, d_vals, d_rev, n_rows, n_cols, nnz, row_offset, row_offset + n_rows, 0, 0,
+                                  side_split, stream);
+}
+
+extern "C" int ssl_plan_create_ranges(ssl_plan **out, const int32_t *h_rowptr, const int32_t *d_colidx, const float *d_vals,
+                                      const int32_t *d_rev, int64_t n_rows, int64_t n_cols, int64_t nnz, int64_t a0, int64_t a1,
+                                      int64_t b0, int64_t b1, int64_t side_split, void *stream) {
     SSL_CHECK_ARG(out && h_rowptr, "ssl_plan_create: null argument");
     SSL_CHECK_ARG(nnz == 0 || (d_colidx && d_vals), "ssl_plan_create: null CSR arrays");
     SSL_CHECK_ARG(n_rows >= 0 && n_cols > 0 && nnz >= 0 && nnz < (int64_t)INT32_MAX, "ssl_plan_create: bad sizes");
+    SSL_CHECK_ARG(0 <= a0 && a0 <= a1 && 0 <= b0 && b0 <= b1 && (a1 - a0) + (b1 - b0) == n_rows && a1 <= n_cols && b1 <= n_cols &&
+                      (b1 == b0 || a1 <= b0),
+                  "ssl_plan_create: the row ranges [%lld,%lld) + [%lld,%lld) must be ascending, disjoint and cover n_rows = %lld",
+                  (long long)a0, (long long)a1, (long long)b0, (long long)b1, (long long)n_rows);
     SSL_CHECK_ARG(h_rowptr[0] == 0 && h_rowptr[n_rows] == nnz, "ssl_plan_create: rowptr does not span nnz");
+    const int64_t split_range = a1 - a0;                     // local rows [0, split_range) are range a
+    auto global_row = [&](int64_t r) { return r < split_range ? a0 + r : b0 + (r - split_range); };
     cudaStream_t st = (cudaStream_t)stream;
 
     // ---- host work list: split long rows, then whole rows by descending degree (counting sort) ----
     std::vector<int4> items;
     std::vector<int2> longs;
     // two sides (rows before / from side_split), each ordered by descending degree: bucket index = side * (kMinSeg+1) + (kMinSeg - deg)
-    const int64_t local_split = std::min<int64_t>(std::max<int64_t>(side_split - row_offset, 0), n_rows);
     const int n_bucket = 2 * (kMinSeg + 1);
     std::vector<int64_t> bucket(n_bucket + 1, 0);
-    auto bucket_of = [&](int64_t r, int64_t deg) { return (int)((r < local_split ? 0 : 1) * (kMinSeg + 1) + (kMinSeg - deg)); };
+    auto bucket_of = [&](int64_t r, int64_t deg) { return (int)((global_row(r) < side_split ? 0 : 1) * (kMinSeg + 1) + (kMinSeg - deg)); };
     int64_t max_deg = 0;
     for (int64_t r = 0; r < n_rows; ++r) {
         const int64_t deg = (int64_t)h_rowptr[r + 1] - h_rowptr[r];
@@ -281,7 +331,8 @@ extern "C" int ssl_plan_create(ssl_plan **out, const int32_t *h_rowptr, const in
         return SSL_E_ALLOC;
     }
     *p = ssl_plan{};
-    p->n_rows = n_rows; p->n_cols = n_cols; p->nnz = nnz; p->row_offset = row_offset;
+    p->n_rows = n_rows; p->n_cols = n_cols; p->nnz = nnz; p->row_offset = a0;
+    p->split_local = split_range; p->off_a = a0; p->off_b = b0 - split_range;
     p->colidx = d_colidx; p->vals = d_vals; p->rev = d_rev;
     p->n_items = (int64_t)items.size(); p->n_long = (int64_t)longs.size(); p->n_slots = n_slots; p->max_deg = max_deg;
     auto fail = [&](cudaError_t e, const char *what) {
@@ -297,15 +348,25 @@ extern "C" int ssl_plan_create(ssl_plan **out, const int32_t *h_rowptr, const in
     }
     if (p->n_long) {
         if ((e = cudaMalloc(&p->long_info, sizeof(int2) * p->n_long)) != cudaSuccess) return fail(e, "cudaMalloc long_info");
-        if ((e = cudaMalloc(&p->counters, sizeof(int32_t) * p->n_long)) != cudaSuccess) return fail(e, "cudaMalloc counters");
+        if ((e = cudaMalloc(&p->counters, sizeof(int32_t) * p->n_long * SSL_MAX_VIEWS)) != cudaSuccess) return fail(e, "cudaMalloc counters");
         if ((e = cudaMalloc(&p->partial, sizeof(float) * kPartialStride * p->n_slots)) != cudaSuccess) return fail(e, "cudaMalloc partial");
         if ((e = cudaMemcpyAsync(p->long_info, longs.data(), sizeof(int2) * p->n_long, cudaMemcpyHostToDevice, st)) != cudaSuccess)
             return fail(e, "copy long_info");
-        if ((e = cudaMemsetAsync(p->counters, 0, sizeof(int32_t) * p->n_long, st)) != cudaSuccess) return fail(e, "memset counters");
+        if ((e = cudaMemsetAsync(p->counters, 0, sizeof(int32_t) * p->n_long * SSL_MAX_VIEWS, st)) != cudaSuccess) return fail(e, "memset counters");
     }
     if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return fail(e, "synchronize");   // host vectors die here
     *out = p;
     return SSL_OK;
+}
+
+extern "C" int ssl_set_option(const char *name, int64_t value) {
+    SSL_CHECK_ARG(name != nullptr, "ssl_set_option: null name");
+    if (std::string(name) == "prop_interleaved") {
+        g_force_interleaved = value != 0;
+        return SSL_OK;
+    }
+    ssl::set_error("ssl_set_option: unknown option '%s'", name);
+    return SSL_E_ARG;
 }
 
 extern "C" int ssl_plan_destroy(ssl_plan *p) {
@@ -344,13 +405,21 @@ extern "C" int ssl_propagate_layer(const ssl_plan *plan, const ssl_prop_args *ar
     }
     for (int i = 0; i < a.n_sum_src; ++i)
         SSL_CHECK_ARG(a.sum_src[i] && (a.sum_src_views[i] == 1 || a.sum_src_views[i] == a.n_views), "ssl_propagate_layer: bad sum_src %d", i);
+    SSL_CHECK_ARG(a.n_peers >= 0 && a.n_peers <= SSL_MAX_PEERS, "ssl_propagate_layer: n_peers %d out of range", a.n_peers);
+    for (int q = 0; q < a.n_peers; ++q) {
+        SSL_CHECK_ARG(a.x_out == nullptr || a.x_out_peers[q] != nullptr, "ssl_propagate_layer: x_out_peers[%d] is null", q);
+        SSL_CHECK_ARG(a.sum_out == nullptr || a.sum_out_peers[q] != nullptr, "ssl_propagate_layer: sum_out_peers[%d] is null", q);
+    }
+    SSL_CHECK_ARG(plan->n_cols + (int64_t)1 < ((int64_t)1 << 32), "ssl_propagate_layer: node ids must fit 32 bits");
     const int mode = any_edge ? 2 : ((a.in_views == 1) ? 0 : 1);
+    // view-major: per-view inputs (mode 1 / 2 with more than one view) and no cross-view reduction in the epilogue
+    const bool view_major = a.n_views > 1 && !a.reduce_views && (mode == 2 || a.in_views == a.n_views) && !g_force_interleaved;
     cudaStream_t st = (cudaStream_t)stream;
     const int quads = a.dim / 4;
-    if (quads <= 4) return launch_g<4>(plan, a, mode, st);
-    if (quads <= 8) return launch_g<8>(plan, a, mode, st);
-    if (quads <= 16) return launch_g<16>(plan, a, mode, st);
-    return launch_g<32>(plan, a, mode, st);
+    if (quads <= 4) return launch_g<4>(plan, a, mode, view_major, st);
+    if (quads <= 8) return launch_g<8>(plan, a, mode, view_major, st);
+    if (quads <= 16) return launch_g<16>(plan, a, mode, view_major, st);
+    return launch_g<32>(plan, a, mode, view_major, st);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -255,7 +255,8 @@ class Propagation:
         self.sum_layers = self.n_layers if sum_layers is None else int(sum_layers)
         self.keep_layers = set(int(k) for k in keep_layers)
         self.noise_eps = float(noise_eps)
-        self.comm = comm       # row-sharded propagation: object with .allgather_rows(local [block, V, d]) -> full
+        self.comm = comm       # parallel.RowShard with shard_propagation: layer outputs live in shared tables, rows are
+                               # exchanged by the kernel's peer stores (or an all-gather) after every launch
         self.loss_comm = loss_comm if loss_comm is not None else comm    # shards the InfoNCE table rows
         if not 1 <= len(self.views) <= _lib.MAX_VIEWS:
             raise ValueError('1..%d views' % _lib.MAX_VIEWS)
@@ -304,11 +305,40 @@ class Propagation:
         seeds = (C.c_uint64 * V)(*[v.seed for v in self.views])
         n = out.shape[0] if backward else x.shape[0]
         with torch.cuda.device(x.device):
+            # the table is full height on every rank (a row-sharded plan shards the SpMM, not NodeDrop): the RNG is keyed by
+            # the global row, so the offset of row 0 is 0 whatever the plan owns
             check(lib.ssl_node_drop(x.data_ptr(), out.data_ptr(), n, x.shape[-1], V, int(backward), mode, keep, masks, seeds,
-                                    self.plan.row_offset, _stream(x)), 'ssl_node_drop')
+                                    0, _stream(x)), 'ssl_node_drop')
 
-    def _gather(self, local: torch.Tensor) -> torch.Tensor:
-        return local if self.comm is None else self.comm.allgather_rows(local)
+    # ---- output tables ---------------------------------------------------------------------------
+    def _out(self, key, shape, ref: torch.Tensor):
+        """A full-height output table: plain memory on one GPU, a persistent shared table (parallel.SharedTable) when the
+        propagation is row-sharded.  Returns (tensor, shared table or None)."""
+        if self.comm is None:
+            return torch.empty(shape, device=ref.device, dtype=torch.float32), None
+        tb = self.comm.table(key, shape, ref.device)
+        return tb.t, tb
+
+    @staticmethod
+    def _set_peers(a: PropArgs, field: str, tb) -> None:
+        if tb is None or not tb.peer_ptrs:
+            return
+        a.n_peers = len(tb.peer_ptrs)
+        arr = getattr(a, field)
+        for q, ptr in enumerate(tb.peer_ptrs):
+            arr[q] = ptr
+
+    def _exchange(self, tables) -> None:
+        """Complete the tables a launch wrote (owned rows -> every rank)."""
+        tables = [tb for tb in tables if tb is not None]
+        if self.comm is None or not tables:
+            return
+        with _timed('prop_exchange', dict(tables=len(tables))):
+            if self.comm.transport == 'symm':
+                self.comm.barrier()                      # the rows travelled with the kernel's stores
+            else:
+                for tb in tables:
+                    self.comm.sync_rows(tb)
 
     # ---- forward -------------------------------------------------------------------------------
     def forward(self, e0: torch.Tensor, n_user: int) -> PropState:
@@ -316,11 +346,13 @@ class Propagation:
         _require_cuda(e0, 'embedding table')
         if not e0.is_contiguous():
             raise RuntimeError('embedding table must be contiguous')
+        if self.sum_layers == 0:
+            raise ValueError('sum_layers must be >= 1')
         st = PropState(self, e0, n_user)
         N, d, V = e0.shape[0], e0.shape[1], len(self.views)
-        r0, nl = self.plan.row_offset, self.plan.n_rows
+        if self.plan.n != N:
+            raise RuntimeError(f'plan is for {self.plan.n} nodes, the table has {N} rows')
         opts = dict(device=e0.device, dtype=torch.float32)
-        nalloc = nl if self.comm is None else self.comm.block
         if self.any_node:
             x0 = torch.empty(N, V, d, **opts)
             self._node_drop(e0, x0, backward=False)
@@ -330,43 +362,41 @@ class Propagation:
             x_prev, in_views = e0, 1
             srcs = [(e0, 1)]
         st.x0 = x_prev
-        E_loc = None
         for k in range(1, self.n_layers + 1):
             a = self._args(d, k, transpose=False)
             a.in_views = in_views
             a.x_in = x_prev.data_ptr()
             need_out = (k < self.n_layers) or (k in self.keep_layers)
-            x_out = torch.empty(nalloc, V, d, **opts) if need_out else None
-            a.x_out = _ptr(x_out)
+            x_out = x_tb = e_tb = None
+            if need_out:
+                x_out, x_tb = self._out(('x', k), (N, V, d), e0)
+                a.x_out = x_out.data_ptr()
+                self._set_peers(a, 'x_out_peers', x_tb)
             if k == self.sum_layers:
-                E_loc = torch.empty(nalloc, V, d, **opts)
-                a.sum_out = E_loc.data_ptr()
+                st.E, e_tb = self._out('E', (N, V, d), e0)
+                a.sum_out = st.E.data_ptr()
+                self._set_peers(a, 'sum_out_peers', e_tb)
                 a.n_sum_src = len(srcs)
                 for i, (s, sv) in enumerate(srcs):
-                    a.sum_src[i] = s.data_ptr() + 4 * (r0 * sv * d)
+                    a.sum_src[i] = s.data_ptr()
                     a.sum_src_views[i] = sv
             self._launch(a, e0)
+            self._exchange([x_tb, e_tb])
             if x_out is not None:
-                x_full = self._gather(x_out)
                 if k in self.keep_layers:
-                    st.layers[k] = x_full
+                    st.layers[k] = x_out
                 if k < self.sum_layers:
-                    srcs.append((x_full, V))
-                x_prev, in_views = x_full, V
-        if self.sum_layers == 0:
-            raise ValueError('sum_layers must be >= 1')
-        st.E = self._gather(E_loc)
+                    srcs.append((x_out, V))
+                x_prev, in_views = x_out, V
         return st
 
     # ---- backward ------------------------------------------------------------------------------
     def backward(self, st: PropState) -> torch.Tensor:
-        """Consumes the sinks of ``st``; returns dE0 [N, d] (full; every rank computes its rows and
-        the row blocks are all-gathered)."""
+        """Consumes the sinks of ``st``; returns dE0 [N, d].  Row-sharded: only the rows this rank owns are computed
+        (the others are zero) -- the sharded Adam updates exactly those and stores them to the peers."""
         e0 = st.e0
         N, d, V = st.n, st.dim, st.n_views
-        r0, nl = self.plan.row_offset, self.plan.n_rows
         opts = dict(device=e0.device, dtype=torch.float32)
-        nalloc = nl if self.comm is None else self.comm.block
         L, S = self.n_layers, self.sum_layers
 
         def residual(k: int) -> Optional[torch.Tensor]:
@@ -399,37 +429,27 @@ class Propagation:
             a.x_in = D.data_ptr()
             res = residual(k - 1)
             if res is not None:
-                a.residual = res.data_ptr() + 4 * (r0 * V * d)
+                a.residual = res.data_ptr()
             last = (k == 1)
             if last and not self.any_node:
-                out = torch.empty(nalloc, d, **opts)
+                out = torch.empty(N, d, **opts) if self.comm is None else torch.zeros(N, d, **opts)
                 a.sum_out, a.reduce_views = out.data_ptr(), 1
                 if g_e0 is not None:
-                    a.reg_src, a.reg_coef = g_e0.data_ptr() + 4 * (r0 * d), 1.0
+                    a.reg_src, a.reg_coef = g_e0.data_ptr(), 1.0
                 self._launch(a, e0)
-                return self._gather_2d(out)
-            x_out = torch.empty(nalloc, V, d, **opts)
+                return out
+            x_out, x_tb = self._out(('d', k % 2), (N, V, d), e0)
             a.x_out = x_out.data_ptr()
+            self._set_peers(a, 'x_out_peers', x_tb)
             self._launch(a, e0)
-            D = self._gather(x_out)
+            self._exchange([x_tb])
+            D = x_out
         return self._node_bwd(D, g_e0, e0)
 
     def _node_bwd(self, d0: torch.Tensor, g_e0: Optional[torch.Tensor], e0: torch.Tensor) -> torch.Tensor:
         out = g_e0.clone() if g_e0 is not None else torch.zeros_like(e0)
         self._node_drop(d0, out, backward=True)
         return out
-
-    def _own_block(self, full: torch.Tensor) -> torch.Tensor:
-        c = self.comm
-        blk = torch.zeros((c.block,) + tuple(full.shape[1:]), device=full.device, dtype=full.dtype) if c.n_local < c.block \
-            else torch.empty((c.block,) + tuple(full.shape[1:]), device=full.device, dtype=full.dtype)
-        blk[:c.n_local].copy_(full[c.r0:c.r1])
-        return blk
-
-    def _gather_2d(self, local: torch.Tensor) -> torch.Tensor:
-        if self.comm is None:
-            return local
-        return self.comm.allgather_rows(local.unsqueeze(1)).squeeze(1)
 
 
 class _PropFn(torch.autograd.Function):
@@ -482,6 +502,8 @@ class _SpmmFn(torch.autograd.Function):
 
 def _spmm_once(plan: GraphPlan, x: torch.Tensor, view: ViewSpec, layer: int, transpose: bool) -> torch.Tensor:
     _require_cuda(x, 'spmm input')
+    if plan.n_rows != plan.n:
+        raise RuntimeError('engine.spmm needs a plan that owns every row (HCCF / LightGCL do not row-shard the propagation)')
     x = x.contiguous()
     prop = Propagation(plan, [view], max(1, layer))
     a = prop._args(x.shape[1], layer, transpose)

@@ -16,58 +16,68 @@ from . import _lib
 
 
 class GraphPlan:
-    """CSR of (a row block of) the normalised adjacency + the native work lists.
+    """CSR of (a row shard of) the normalised adjacency + the native work lists.
 
     rows/cols/vals : COO triplets in ANY order (numpy or torch, host or device).
     n             : number of nodes N = |U| + |I| (matrix is N x N).
-    row_range     : (r0, r1) global rows owned by this plan (row-sharded multi-GPU); default all.
+    row_ranges    : ((a0, a1), (b0, b1)) global rows owned by this plan (row-sharded multi-GPU: the rank's share
+                    of the user rows and of the item rows); ``row_range`` = one range; default all rows.
     ``coo_to_csr`` maps the caller's entry order to CSR positions so masks given in the
     reference's COO order (aug_utils.py:25-30) can be injected.
     """
 
-    def __init__(self, rows, cols, vals, n: int, device: torch.device, row_range=None, need_rev: bool = False, side_split: int = 0):
-        rows = _np(rows).astype(np.int64)
-        cols = _np(cols).astype(np.int64)
-        vals = _np(vals).astype(np.float32)
-        self.n = int(n)
-        self.device = torch.device(device)
-        r0, r1 = (0, self.n) if row_range is None else (int(row_range[0]), int(row_range[1]))
-        self.row_offset, self.n_rows = r0, r1 - r0
-        if row_range is not None:                              # a shard sorts only its own entries
-            sel = (rows >= r0) & (rows < r1)
-            rows, cols, vals = rows[sel], cols[sel], vals[sel]
-        order = np.lexsort((cols, rows))                       # CSR order: row, then col
-        if row_range is None:
+    def __init__(self, rows, cols, vals, n: int, device: torch.device, row_range=None, need_rev: bool = False, side_split: int = 0,
+                 row_ranges=None):
+        n = int(n)
+        sharded = row_range is not None or row_ranges is not None
+        ranges = _ranges(n, row_range, row_ranges)
+        rowptr, rows_s, cols_s, vals_s, order = local_csr(rows, cols, vals, ranges)
+        if not sharded:
             self.coo_to_csr_full = np.empty_like(order)
             self.coo_to_csr_full[order] = np.arange(order.shape[0])
-        rows_s, cols_s, vals_s = rows[order], cols[order], vals[order]
-        self.entry_lo = 0
-        rows_l, cols_l, vals_l = rows_s - r0, cols_s, vals_s
-        self.nnz = int(rows_l.shape[0])
-        rowptr = np.zeros(self.n_rows + 1, dtype=np.int64)
-        rowptr[1:] = np.cumsum(np.bincount(rows_l, minlength=self.n_rows))
-        if self.nnz >= 2 ** 31 - 1:
-            raise ValueError('a plan holds at most 2^31-2 entries; shard the rows')
-        self.h_rowptr = np.ascontiguousarray(rowptr.astype(np.int32))
-        self.colidx = torch.from_numpy(cols_l.astype(np.int32)).to(self.device)
-        self.vals = torch.from_numpy(vals_l).to(self.device)
-        self.rev = None
+        rev = None
         if need_rev:
-            if row_range is not None:
+            if sharded:
                 raise ValueError('injected masks (rev) are a single-GPU debugging aid')
-            key = rows_s * self.n + cols_s
-            keyt = cols_s * self.n + rows_s
+            key = rows_s * n + cols_s
+            keyt = cols_s * n + rows_s
             pos = np.searchsorted(key, keyt)
             if not np.array_equal(key[pos], keyt):
                 raise ValueError('adjacency structure is not symmetric')
-            self.rev = torch.from_numpy(pos.astype(np.int32)).to(self.device)
+            rev = torch.from_numpy(pos.astype(np.int32)).to(device)
+        self._setup(np.ascontiguousarray(rowptr.astype(np.int32)), torch.from_numpy(cols_s.astype(np.int32)).to(device),
+                    torch.from_numpy(vals_s).to(device), n, torch.device(device), ranges, rev, side_split)
+
+    @classmethod
+    def from_csr(cls, h_rowptr, colidx: torch.Tensor, vals: torch.Tensor, n: int, row_ranges=None, side_split: int = 0) -> 'GraphPlan':
+        """From a ready CSR of the owned rows: host int32 rowptr over the local rows (range a then range b), device
+        int32 global column ids (ascending inside a row) and device fp32 values -- no host sort (BASELINE config 4)."""
+        self = cls.__new__(cls)
+        self._setup(np.ascontiguousarray(np.asarray(h_rowptr, dtype=np.int32)), colidx.contiguous(), vals.contiguous(), int(n),
+                    colidx.device, _ranges(int(n), None, row_ranges), None, side_split)
+        return self
+
+    def _setup(self, h_rowptr, colidx, vals, n, device, ranges, rev, side_split):
+        (a0, a1), (b0, b1) = ranges
+        self.n, self.device, self.ranges = n, torch.device(device), ranges
+        self.row_offset, self.n_rows = a0, (a1 - a0) + (b1 - b0)      # row_offset: first owned row (single-range plans)
+        self.entry_lo = 0
+        self.h_rowptr, self.colidx, self.vals, self.rev = h_rowptr, colidx, vals, rev
+        self.nnz = int(colidx.shape[0])
+        if colidx.dtype != torch.int32 or vals.dtype != torch.float32 or h_rowptr.shape[0] != self.n_rows + 1:
+            raise ValueError('CSR arrays must be int32 colidx, fp32 vals, rowptr of n_rows + 1 entries')
         self._handle = C.c_void_p()
         stream = torch.cuda.current_stream(self.device).cuda_stream
         with torch.cuda.device(self.device):
-            _lib.check(_lib.lib.ssl_plan_create(
+            _lib.check(_lib.lib.ssl_plan_create_ranges(
                 C.byref(self._handle), self.h_rowptr.ctypes.data, self.colidx.data_ptr(), self.vals.data_ptr(),
                 self.rev.data_ptr() if self.rev is not None else None,
-                self.n_rows, self.n, self.nnz, self.row_offset, int(side_split), stream), 'ssl_plan_create')
+                self.n_rows, self.n, self.nnz, a0, a1, b0, b1, int(side_split), stream), 'ssl_plan_create_ranges')
+
+    def owned_rows(self) -> torch.Tensor:
+        """Global ids of the owned rows in local order (host int64)."""
+        (a0, a1), (b0, b1) = self.ranges
+        return torch.cat([torch.arange(a0, a1), torch.arange(b0, b1)])
 
     @classmethod
     def from_torch_adj(cls, adj: torch.Tensor, device=None, need_rev: bool = False, side_split: int = 0) -> 'GraphPlan':
@@ -103,6 +113,36 @@ class GraphPlan:
                 self._handle = C.c_void_p()
         except Exception:
             pass
+
+
+def local_csr(rows, cols, vals, ranges):
+    """Host part of a (sharded) plan: the COO entries whose row lies in ``ranges`` = ((a0, a1), (b0, b1)), sorted into CSR
+    order over the local rows (range a, then range b).  -> (rowptr int64 [n_local + 1], global rows, cols, vals of the
+    kept entries in CSR order, and ``order``: positions of those entries in the caller's arrays)."""
+    rows = _np(rows).astype(np.int64)
+    cols = _np(cols).astype(np.int64)
+    vals = _np(vals).astype(np.float32)
+    (a0, a1), (b0, b1) = ranges
+    keep = np.flatnonzero(((rows >= a0) & (rows < a1)) | ((rows >= b0) & (rows < b1)))
+    order = keep[np.lexsort((cols[keep], rows[keep]))]          # CSR order: row, then col (range a precedes range b)
+    rows_s, cols_s, vals_s = rows[order], cols[order], vals[order]
+    rows_l = np.where(rows_s < a1, rows_s - a0, rows_s - b0 + (a1 - a0))
+    n_rows = (a1 - a0) + (b1 - b0)
+    rowptr = np.zeros(n_rows + 1, dtype=np.int64)
+    rowptr[1:] = np.cumsum(np.bincount(rows_l, minlength=n_rows))
+    if rows_l.shape[0] >= 2 ** 31 - 1:
+        raise ValueError('a plan holds at most 2^31-2 entries; shard the rows')
+    return rowptr, rows_s, cols_s, vals_s, order
+
+
+def _ranges(n, row_range, row_ranges):
+    if row_ranges is not None:
+        (a0, a1), (b0, b1) = row_ranges
+        if b1 == b0:
+            b0 = b1 = a1
+        return (int(a0), int(a1)), (int(b0), int(b1))
+    r0, r1 = (0, n) if row_range is None else (int(row_range[0]), int(row_range[1]))
+    return (r0, r1), (r1, r1)
 
 
 def _np(x) -> np.ndarray:

@@ -3,14 +3,21 @@ amsgrad) as ONE pass over (p, g, m, v) per parameter with the native kernel; whe
 adjacent views of a flat table and so are their gradients, one launch covers them all."""
 from __future__ import annotations
 
+import ctypes as C
+
 import torch
 
 from ._lib import check, lib
 
 
 class FusedAdam(torch.optim.Optimizer):
-    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, row_shards=None, comm=None):
+        """row_shards / comm (row-sharded multi-GPU, BaseModel.shard_to): {id(param): (lo, hi, peer base addresses)} -- such a
+        parameter is updated on its owned rows [lo, hi) only and the new values are stored to the same rows of every
+        peer's replica by the kernel (the all-gather of the updated table, fused into the optimizer)."""
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+        self.row_shards = dict(row_shards or {})          # keyed by id(param)
+        self.comm = comm
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -34,11 +41,46 @@ class FusedAdam(torch.optim.Optimizer):
                 st['step'] += 1
                 g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
                 todo.append((p, g, st))
+            sharded = [p for p, _, _ in todo if id(p) in self.row_shards]
+            if sharded and self.comm is not None:
+                self.comm.barrier()          # every rank has finished reading the old parameters (backward) before any peer store
+            from . import engine
+            timed = engine._timed('adam', dict(params=len(todo), sharded=len(sharded)))
+            timed.__enter__()
             for p, g, st in todo:
                 if not p.is_contiguous():
                     raise RuntimeError('FusedAdam: parameters must be contiguous')
                 with torch.cuda.device(p.device):
-                    check(lib.ssl_adam_step(p.data_ptr(), g.data_ptr(), st['exp_avg'].data_ptr(), st['exp_avg_sq'].data_ptr(),
-                                            p.numel(), st['step'], group['lr'], b1, b2, group['eps'], group['weight_decay'],
-                                            torch.cuda.current_stream(p.device).cuda_stream), 'ssl_adam_step')
+                    stream = torch.cuda.current_stream(p.device).cuda_stream
+                    if id(p) in self.row_shards:
+                        lo, hi, peers = self.row_shards[id(p)]
+                        w = p.shape[1] if p.dim() > 1 else 1
+                        off = 4 * lo * w
+                        arr = (C.c_void_p * max(1, len(peers)))(*[q + off for q in peers])
+                        check(lib.ssl_adam_step_peers(p.data_ptr() + off, arr, len(peers), g.data_ptr() + off, st['exp_avg'].data_ptr() + off,
+                                                      st['exp_avg_sq'].data_ptr() + off, (hi - lo) * w, st['step'], group['lr'], b1, b2,
+                                                      group['eps'], group['weight_decay'], stream), 'ssl_adam_step_peers')
+                    else:
+                        check(lib.ssl_adam_step(p.data_ptr(), g.data_ptr(), st['exp_avg'].data_ptr(), st['exp_avg_sq'].data_ptr(),
+                                                p.numel(), st['step'], group['lr'], b1, b2, group['eps'], group['weight_decay'], stream),
+                              'ssl_adam_step')
+            timed.__exit__(None, None, None)
+            if sharded and self.comm is not None:
+                self._after_sharded_step(sharded)
         return loss
+
+    def _after_sharded_step(self, params):
+        """symm transport: the new rows are already in the peers' replicas -> barrier.  nccl transport: all-gather the owned
+        row blocks of each parameter."""
+        if self.comm.transport == 'symm':
+            self.comm.barrier()
+            return
+        dist, world = self.comm.dist, self.comm.world
+        for p in params:
+            lo, hi, _ = self.row_shards[id(p)]
+            blk = (p.shape[0] + world - 1) // world
+            local = torch.zeros((blk,) + tuple(p.shape[1:]), device=p.device, dtype=p.dtype)
+            local[:hi - lo].copy_(p.data[lo:hi])
+            full = torch.empty((world * blk,) + tuple(p.shape[1:]), device=p.device, dtype=p.dtype)
+            dist.all_gather_into_tensor(full, local)
+            p.data.copy_(full[:p.shape[0]])

@@ -1,43 +1,75 @@
-"""Row-sharded multi-GPU execution: the adjacency rows and every [N, V, d]
-layer output are split into ``world`` contiguous row blocks, one per GPU (one process per GPU,
-``torch.distributed`` NCCL over NVLink 5 / NVSwitch).
+"""Row-sharded multi-GPU execution (BASELINE.json north_star): one process per
+GPU, ``torch.distributed`` for the plumbing, the data path in the library's own kernels.
 
-Exchange steps -- the only collectives on the path:
-  * one all-gather of the [N/world, V, d] layer output per propagation layer, forward and backward
-    (each rank computes its rows from the full previous layer);
+Partition.  Every GPU owns the same share of BOTH sides of the bipartite graph: user rows
+[u0, u1) and item rows [|U| + i0, |U| + i1) (equal blocks of ceil(n_side / world) rows), so the stored
+entries -- half of which sit in the item rows -- are balanced; a contiguous split of the N rows would give the
+last rank every item row (half of all entries at BASELINE config 4).  Each GPU keeps FULL [N, V, d]
+tables (180 GB of HBM per GPU: the 6 GB tables of config 4 are replicated, the CSR is not) and computes
+only the rows it owns from a full copy of the previous layer.
+
+Exchange steps -- the only inter-GPU traffic on the path:
+  * per propagation layer and direction the all-gather of the d-wide layer output.  With the
+    ``symm`` transport it is FUSED INTO THE SpMM: the tables live in symmetric memory (every rank maps
+    every peer's allocation over NVLink), the kernel's epilogue stores each finished row to the same
+    row of all peers' tables (``ssl_prop_args.x_out_peers``), so the NVLink traffic overlaps the
+    gathers of the rows still being computed; what remains is a cross-GPU barrier on the stream after the
+    launch.  The ``nccl`` transport (fallback, and the gloo CPU tests) all-gathers the owned row
+    blocks with ``all_gather_into_tensor`` after the launch;
+  * the updated parameters: Adam runs on the owned rows only and stores the new values to every peer's
+    replica of the table (``ssl_adam_step_peers``) -- the sixth all-gather of a step, fused the same way;
   * per InfoNCE term one all-reduce of the per-anchor partial (row sum, weighted table average)
     [B, d+1], because the table rows (negatives) are sharded and the anchors are replicated, and in the
-    backward one all-gather of the [N_side/world, d] dense table-gradient blocks;
-  * one all-gather of the [N/world, d] gradient block before the (replicated) Adam step.
-The propagation all-gathers only happen when the propagation itself is sharded (``shard_propagation``:
-automatic by table size); small graphs replicate the sub-millisecond SpMM and shard only the loss.
-Blocks are equal-sized (ceil(N / world), the last one padded) so the gathered buffer's first N rows
-ARE the full tensor -- no compaction copy.  Everything else (BPR on the replicated batch, the
-regulariser, Adam on the replicated table) is rank-local and bit-identical across ranks.
+    backward one all-gather of the [N_side/world, d] dense table-gradient blocks.
+Propagation is sharded only when ``shard_propagation`` (automatic by table size): for the bundled-dataset
+shapes a layer takes ~0.15 ms while its all-gather would move the whole 123 MB layer, so there the SpMM is
+replicated and only the loss is sharded.  BPR on the replicated batch and the regulariser are rank-local
+and bit-identical across ranks.
 
 ``BatchShard`` is the other way to use N GPUs: the batches are the sharded unit.  Every rank runs the
 whole step on its OWN batch of B samples and the only exchange is one all-reduce (average) of the
-parameter gradients before the Adam step.  Every loss term of the path is a batch sum divided by the
-batch size (lightgcn.py:52, simgcl.py:48-50, sgl.py:56-60, ncl.py:58,68,82) or does not depend on
-the batch (reg_params), and the in-kernel augmentation draws are keyed by the shared seed, so the
-averaged gradient IS the gradient of one reference step at ``batch_size = world * B``: the optimiser
-trajectory is that of the reference with the larger batch, and the parameters stay identical on all
-ranks.  (HCCF's contrastive term averages over the batch's UNIQUE nodes, hccf.py:80-81, so there the
-average of per-rank terms is the usual data-parallel approximation, not an identity.)
+parameter gradients before the Adam step.  For LightGCN, SimGCL, SGL and NCL every loss term is a batch
+sum divided by the batch size (lightgcn.py:52, simgcl.py:48-50, sgl.py:56-60, ncl.py:58,68,82) or does
+not depend on the batch (reg_params), and the in-kernel augmentation draws are keyed by the shared seed, so
+the averaged gradient IS the gradient of one reference step at ``batch_size = world * B``.  It is the usual
+data-parallel APPROXIMATION (not an identity) for HCCF (its contrastive term averages over the batch's
+unique nodes, hccf.py:80-81, and F.dropout draws per rank), for DirectAU (uniformity is the log of a
+per-batch pair mean, loss_utils.py:82-86) and for NCL's k-means initialisation unless the torch seeds are in
+lock-step.
 """
 from __future__ import annotations
+
+from typing import Dict, List, Optional, Tuple
 
 import torch
 
 from .graph import GraphPlan
 
 
+def block_range(n: int, world: int, rank: int) -> Tuple[int, int]:
+    """Rank's share of n rows cut into ``world`` equal blocks of ceil(n / world) (the last ones short or empty)."""
+    blk = (n + world - 1) // world
+    lo = min(n, rank * blk)
+    return lo, min(n, lo + blk)
+
+
+class SharedTable:
+    """A [N, ...] fp32 table that exists on every rank at the same logical address: ``t`` is this rank's copy,
+    ``peer_ptrs`` the device addresses of the OTHER ranks' copies as mapped into this process (empty for the
+    nccl transport)."""
+
+    def __init__(self, t: torch.Tensor, peer_ptrs: List[int], handle=None):
+        self.t, self.peer_ptrs, self.handle = t, peer_ptrs, handle
+
+
 class RowShard:
-    def __init__(self, dist, rank: int, world: int, n: int, shard_propagation='auto', dim: int = 64, views: int = 3):
+    def __init__(self, dist, rank: int, world: int, n: int, shard_propagation='auto', dim: int = 64, views: int = 3,
+                 n_user: Optional[int] = None, transport: str = 'auto'):
         self.dist, self.rank, self.world, self.n = dist, rank, world, n
-        self.block = (n + world - 1) // world
-        self.r0 = min(n, rank * self.block)
-        self.r1 = min(n, self.r0 + self.block)
+        self.n_user = n if n_user is None else int(n_user)          # None: one side only (a contiguous block of rows)
+        self.u0, self.u1 = block_range(self.n_user, world, rank)
+        i0, i1 = block_range(n - self.n_user, world, rank)
+        self.i0, self.i1 = self.n_user + i0, self.n_user + i1
         # Row-sharding the propagation costs one all-gather of the whole [N, V, d] layer per layer and
         # direction; it pays when the SpMM is long (HBM-bound tables far beyond L2, BASELINE.json config 4),
         # not when a layer takes ~0.2 ms (the bundled datasets).  The contraction of the contrastive loss
@@ -45,27 +77,80 @@ class RowShard:
         if shard_propagation == 'auto':
             shard_propagation = n * views * dim * 4 >= (1 << 30)
         self.shard_propagation = bool(shard_propagation)
+        if transport == 'auto':
+            transport = 'symm' if (dist.get_backend() == 'nccl' and world <= 8) else 'nccl'
+        if transport not in ('symm', 'nccl'):
+            raise ValueError("transport must be 'symm' (fused NVLink stores) or 'nccl' (all_gather after the launch)")
+        self.transport = transport
+        self._tables: Dict[tuple, SharedTable] = {}
+        self._barrier_handle = None
+        self.stats = dict(barriers=0, gathers=0, gathered_bytes=0)
+
+    # ---- ownership -----------------------------------------------------------------------------
+    @property
+    def ranges(self):
+        return (self.u0, self.u1), (self.i0, self.i1)
 
     @property
     def n_local(self) -> int:
-        return self.r1 - self.r0
+        return (self.u1 - self.u0) + (self.i1 - self.i0)
 
     def make_plan(self, adj: torch.Tensor, device, side_split: int = 0) -> GraphPlan:
         idx, val = adj._indices(), adj._values()
         return GraphPlan(idx[0].cpu().numpy(), idx[1].cpu().numpy(), val.cpu().numpy(), adj.shape[0], device,
-                         row_range=(self.r0, self.r1), side_split=side_split)
+                         row_ranges=self.ranges, side_split=side_split)
 
-    def alloc_rows(self, *tail, device, dtype=torch.float32) -> torch.Tensor:
-        """Local output buffer with ``block`` rows (>= n_local) so it can be all-gathered in place."""
-        return torch.empty(self.block, *tail, device=device, dtype=dtype)
+    # ---- shared tables -------------------------------------------------------------------------
+    def table(self, key, shape, device) -> SharedTable:
+        """Persistent [N, ...] fp32 table named ``key`` (allocated collectively on first use: every rank must ask for
+        the same keys in the same order)."""
+        k = (key, tuple(shape))
+        tb = self._tables.get(k)
+        if tb is None:
+            tb = self._alloc(tuple(shape), device)
+            self._tables[k] = tb
+        return tb
 
-    def allgather_rows(self, local: torch.Tensor) -> torch.Tensor:
-        """local [block, ...] (rows beyond n_local are padding) -> full [N, ...] on every rank."""
-        assert local.shape[0] == self.block and local.is_contiguous()
-        out = torch.empty((self.world * self.block,) + tuple(local.shape[1:]), device=local.device, dtype=local.dtype)
-        self.dist.all_gather_into_tensor(out, local)
-        return out[:self.n]
+    def _alloc(self, shape, device) -> SharedTable:
+        if self.transport == 'symm':
+            import torch.distributed._symmetric_memory as symm
+            t = symm.empty(shape, dtype=torch.float32, device=device)
+            hdl = symm.rendezvous(t, self.dist.group.WORLD.group_name)
+            ptrs = [int(p) for q, p in enumerate(hdl.buffer_ptrs) if q != self.rank]
+            if self._barrier_handle is None:
+                self._barrier_handle = hdl
+            return SharedTable(t, ptrs, hdl)
+        return SharedTable(torch.empty(shape, dtype=torch.float32, device=device), [])
 
+    def sync_rows(self, tb: SharedTable) -> None:
+        """After a launch that wrote the owned rows of ``tb``: make every rank's copy complete.  symm: the rows are
+        already on their way to the peers (stores issued by the kernel), so a cross-GPU barrier on the stream is all
+        that is left; nccl: all-gather the owned row blocks of both sides."""
+        if self.transport == 'symm':
+            self.barrier()
+            return
+        t = tb.t
+        for lo, hi, side_lo, n_side in ((self.u0, self.u1, 0, self.n_user), (self.i0, self.i1, self.n_user, self.n - self.n_user)):
+            if n_side == 0:
+                continue
+            blk = (n_side + self.world - 1) // self.world
+            local = torch.zeros((blk,) + tuple(t.shape[1:]), device=t.device, dtype=t.dtype)
+            local[:hi - lo].copy_(t[lo:hi])
+            full = torch.empty((self.world * blk,) + tuple(t.shape[1:]), device=t.device, dtype=t.dtype)
+            self.dist.all_gather_into_tensor(full, local)
+            t[side_lo:side_lo + n_side].copy_(full[:n_side])
+            self.stats['gathers'] += 1
+            self.stats['gathered_bytes'] += full.numel() * 4
+
+    def barrier(self) -> None:
+        """Cross-GPU barrier ordered on the current stream (no host synchronisation with the symm transport)."""
+        self.stats['barriers'] += 1
+        if self.transport == 'symm' and self._barrier_handle is not None:
+            self._barrier_handle.barrier(channel=0)
+        else:
+            self.dist.barrier()
+
+    # ---- loss sharding (InfoNCE table rows) -------------------------------------------------------
     def allreduce_sum(self, t: torch.Tensor) -> torch.Tensor:
         self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
         return t

@@ -4,6 +4,10 @@ same loop: sample_negs, zero_grad, cal_loss, loss.item(), backward, step, per-te
 ``evaluate`` (:139-152 + metrics.py:82-127 with the native top-k)."""
 from __future__ import annotations
 
+import os
+import time
+from copy import deepcopy
+
 import numpy as np
 import torch
 
@@ -70,24 +74,107 @@ class Trainer(object):
         return ep_loss, loss_log_dict
 
     def train(self, model):
+        """trainer.py:86-137: plain run (evaluate every ``test_step`` epochs, then test + save) or, when the YAML
+        carries ``patience`` (configurator sets ``early_stop``), tracking of the best first-metric@k[0] with the
+        best ``state_dict`` restored into a freshly built model before the final evaluate / test / save."""
         self.create_optimizer(model)
-        for epoch_idx in range(configs['train']['epoch']):
+        cfg = configs['train']
+        if not cfg.get('early_stop', False):
+            for epoch_idx in range(cfg['epoch']):
+                self.train_epoch(model, epoch_idx)
+                if epoch_idx % cfg['test_step'] == 0:
+                    self.evaluate(model, epoch_idx)
+            self.test(model)
+            self.save_model(model)
+            return model
+        key = configs['test']['metrics'][0]
+        waited, best_epoch, best_metric, best_state = 0, 0, -1e9, None
+        for epoch_idx in range(cfg['epoch']):
             self.train_epoch(model, epoch_idx)
-            if epoch_idx % configs['train']['test_step'] == 0 and hasattr(self.data_handler, 'valid_dataloader'):
-                self.evaluate(model, epoch_idx)
+            if epoch_idx % cfg['test_step'] != 0:
+                continue
+            score = self.evaluate(model, epoch_idx)[key][0]
+            if score > best_metric:
+                waited, best_epoch, best_metric = 0, epoch_idx, score
+                best_state = deepcopy(model.state_dict())
+                self._log('Validation score increased.  Copying the best model ...')
+            else:
+                waited += 1
+                self._log(f"Early stop counter: {waited} out of {cfg['patience']}")
+            if waited == cfg['patience']:
+                break
+        self._log('Best Epoch {}'.format(best_epoch))
+        if best_state is not None:
+            model = self._rebuild(model, best_state)
+        self.evaluate(model)
+        self.test(model)
+        self.save_model(model)
+        return model
+
+    def _log(self, msg):
+        if self.logger is not None:
+            self.logger.log(msg)
+
+    def _rebuild(self, model, state_dict):
+        """The reference re-creates the model with build_model(data_handler) and loads the best parameters
+        (trainer.py:129-131); here the same class is re-instantiated on the same data handler."""
+        fresh = type(model)(self.data_handler).to(configs['device'])
+        fresh.comm = getattr(model, 'comm', None)
+        fresh.load_state_dict(state_dict)
+        return fresh
+
+    def test(self, model):
+        """trainer.py:152-160: metrics on the test split."""
+        if not hasattr(self.data_handler, 'test_dataloader'):
+            raise NotImplementedError('data handler has no test_dataloader')
+        return self.evaluate(model, loader=self.data_handler.test_dataloader, data_type='Test set')
+
+    def save_model(self, model):
+        """trainer.py:162-186: ./checkpoint/{model}/{model}-{data}-{timestamp}.pth (tune runs: ./checkpoint/{model}/tune/
+        {model}-{data}-{now_para_str}.pth) when train.save_model is set.  Returns the path or None."""
+        if not configs['train'].get('save_model', False):
+            return None
+        model_name, data_name = configs['model']['name'], configs['data']['name']
+        tune = configs.get('tune', {}).get('enable', False)
+        save_dir = './checkpoint/{}{}'.format(model_name, '/tune' if tune else '')
+        os.makedirs(save_dir, exist_ok=True)
+        tag = configs['tune']['now_para_str'] if tune else int(time.time())
+        path = '{}/{}-{}-{}.pth'.format(save_dir, model_name, data_name, tag)
+        torch.save({k: v.detach().cpu() for k, v in model.state_dict().items()}, path)
+        self._log('Save model parameters to {}'.format(path))
+        return path
+
+    def load_model(self, model):
+        """trainer.py:188-196."""
+        if 'pretrain_path' not in configs['train']:
+            raise KeyError("No pretrain_path in configs['train']")
+        path = configs['train']['pretrain_path']
+        model.load_state_dict(torch.load(path, map_location=configs['device']))
+        self._log('Load model parameters from {}'.format(path))
         return model
 
     @torch.no_grad()
-    def evaluate(self, model, epoch_idx=None, loader=None):
-        """All-rank evaluation: full_predict -> top-max(k) on device -> recall / ndcg on host
-        (metrics.py:82-127, :11-45)."""
+    def evaluate(self, model, epoch_idx=None, loader=None, data_type=None):
+        """All-rank evaluation: full_predict -> top-max(k) on device -> recall / ndcg / precision / mrr on host
+        (metrics.py:11-45, :82-127).  Validation split when the handler has one, else the test split
+        (trainer.py:139-150)."""
         model.eval()
-        loader = loader or getattr(self.data_handler, 'valid_dataloader', None) or self.data_handler.test_dataloader
+        if loader is None:
+            if hasattr(self.data_handler, 'valid_dataloader'):
+                loader, data_type = self.data_handler.valid_dataloader, 'Validation set'
+            elif hasattr(self.data_handler, 'test_dataloader'):
+                loader, data_type = self.data_handler.test_dataloader, 'Test set'
+            else:
+                raise NotImplementedError('data handler has neither valid_dataloader nor test_dataloader')
         ks = configs['test']['k']
         metrics = configs['test']['metrics']
+        unknown = [m for m in metrics if m not in ('recall', 'ndcg', 'precision', 'mrr')]
+        if unknown:
+            raise ValueError(f'unknown test metrics {unknown} (metrics.py knows recall, ndcg, precision, mrr)')
         result = {m: np.zeros(len(ks)) for m in metrics}
         ds = loader.dataset
         n_users = len(ds.test_users)
+        seen = 0
         for tem in loader:
             if not isinstance(tem, (list, tuple)):
                 tem = [tem]
@@ -96,6 +183,7 @@ class Trainer(object):
             if len(batch_data) == 1:
                 batch_data.append('train')                   # dataset built with dense_mask=False: mask from the device CSR
             preds = model.full_predict(batch_data)
+            seen += preds.shape[0]
             top = topk(preds, max(ks)).cpu().numpy()
             for bi, u in enumerate(users):
                 truth = ds.user_pos_lists[u]
@@ -108,8 +196,11 @@ class Trainer(object):
                         result['ndcg'][ki] += (hit[:k] / np.log2(np.arange(2, k + 2))).sum() / idcg / n_users
                     if 'precision' in result:
                         result['precision'][ki] += hit[:k].sum() / k / n_users
+                    if 'mrr' in result:                      # metrics.py:24-29: sum of hit / rank over the top k
+                        result['mrr'][ki] += (hit[:k] / np.arange(1, k + 1)).sum() / n_users
+        assert seen == n_users, 'evaluation did not cover every test user (metrics.py:113)'
         if self.logger is not None:
-            self.logger.log_eval(result, ks, data_type='Validation set', epoch_idx=epoch_idx)
+            self.logger.log_eval(result, ks, data_type=data_type or 'Validation set', epoch_idx=epoch_idx)
         return result
 
 

@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 
 
 def _setup(model_name, graph, hp, seed=7):
-    from sslrec_b200.datagen import named_graph
+    from synth_graphs import named_graph
     rows, cols, U, I = named_graph(graph, seed=2023)
     case = dict(rows=rows, cols=cols, n_user=U, n_item=I, dim=hp['embedding_size'], batch=4096)
     g = torch.Generator().manual_seed(seed)

@@ -22,18 +22,36 @@ def _gloo_worker(rank, world, port, n):
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
     dist.init_process_group('gloo', rank=rank, world_size=world)
     from sslrec_b200.parallel import RowShard
-    sh = RowShard(dist, rank, world, n)
-    full = torch.arange(n * 2 * 3, dtype=torch.float32).view(n, 2, 3)
-    local = torch.zeros(sh.block, 2, 3)
-    local[:sh.n_local] = full[sh.r0:sh.r1]
-    got = sh.allgather_rows(local)
-    assert torch.equal(got, full)
-    # every global row belongs to exactly one rank; side ranges split without gaps
+    n_user = n // 3
+    sh = RowShard(dist, rank, world, n, n_user=n_user, shard_propagation=True)
+    assert sh.transport == 'nccl'            # gloo: collectives after the launch, no peer stores
+    # every global row belongs to exactly one rank, and every rank owns rows of both sides
     owned = torch.zeros(n)
-    owned[sh.r0:sh.r1] = 1
+    (u0, u1), (i0, i1) = sh.ranges
+    owned[u0:u1] += 1
+    owned[i0:i1] += 1
+    assert u1 <= n_user <= i0 and sh.n_local == (u1 - u0) + (i1 - i0)
     dist.all_reduce(owned)
     assert torch.equal(owned, torch.ones(n))
-    n_user = n // 3
+    # a table whose owned rows were written locally becomes complete on every rank
+    full = torch.arange(n * 2 * 3, dtype=torch.float32).view(n, 2, 3)
+    tb = sh.table('x', (n, 2, 3), 'cpu')
+    assert sh.table('x', (n, 2, 3), 'cpu') is tb and not tb.peer_ptrs
+    tb.t.fill_(-1.0)
+    tb.t[u0:u1] = full[u0:u1]
+    tb.t[i0:i1] = full[i0:i1]
+    sh.sync_rows(tb)
+    assert torch.equal(tb.t, full)
+    # the sharded optimizer's parameter exchange (nccl transport path) completes the table the same way
+    from sslrec_b200.optim import FusedAdam
+    p_u, p_i = torch.nn.Parameter(torch.full((n_user, 4), -1.0)), torch.nn.Parameter(torch.full((n - n_user, 4), -1.0))
+    want_u, want_i = torch.arange(n_user * 4.0).view(n_user, 4), 100 + torch.arange((n - n_user) * 4.0).view(n - n_user, 4)
+    p_u.data[u0:u1] = want_u[u0:u1]
+    p_i.data[i0 - n_user:i1 - n_user] = want_i[i0 - n_user:i1 - n_user]
+    opt = FusedAdam([p_u, p_i], row_shards={id(p_u): (u0, u1, []), id(p_i): (i0 - n_user, i1 - n_user, [])}, comm=sh)
+    opt._after_sharded_step([p_u, p_i])
+    assert torch.equal(p_u.data, want_u) and torch.equal(p_i.data, want_i)
+    # InfoNCE table sharding: side ranges split without gaps
     lo_u, hi_u = sh.side_range(0, n_user)
     lo_i, hi_i = sh.side_range(n_user, n - n_user)
     cnt = torch.tensor([hi_u - lo_u, hi_i - lo_i], dtype=torch.float32)
@@ -57,6 +75,28 @@ def _gloo_worker(rank, world, port, n):
 @pytest.mark.parametrize('n', [10, 11, 64])
 def test_row_shard_plumbing_gloo_world2(n):
     mp.spawn(_gloo_worker, args=(2, _free_port(), n), nprocs=2, join=True)
+
+
+def test_local_csr_of_two_row_ranges():
+    """Host side of a sharded plan: the entries of the owned user + item rows in CSR order over the local rows."""
+    from sslrec_b200.graph import local_csr
+    rs = np.random.RandomState(0)
+    n = 50
+    rows, cols = rs.randint(0, n, 400), rs.randint(0, n, 400)
+    key = np.unique(rows * n + cols)
+    rows, cols = key // n, key % n
+    perm = rs.permutation(len(rows))
+    rows, cols = rows[perm], cols[perm]
+    vals = rs.rand(len(rows)).astype(np.float32)
+    ranges = ((5, 12), (30, 41))
+    rowptr, rows_s, cols_s, vals_s, order = local_csr(rows, cols, vals, ranges)
+    owned = list(range(5, 12)) + list(range(30, 41))
+    assert rowptr.shape[0] == len(owned) + 1 and rowptr[-1] == len(rows_s)
+    for li, r in enumerate(owned):
+        seg = slice(rowptr[li], rowptr[li + 1])
+        want = np.sort(cols[rows == r])
+        assert np.array_equal(cols_s[seg], want) and np.all(rows_s[seg] == r)
+    assert np.array_equal(vals[order], vals_s) and np.array_equal(rows[order], rows_s)
 
 
 def _dp_gloo_worker(rank, world, port):
@@ -138,6 +178,8 @@ def test_data_parallel_step_matches_big_batch():
 
 
 def _gpu_worker(rank, world, port, out):
+    """Row-sharded steps (loss-only sharding; sharded propagation with the fused NVLink stores and with the NCCL
+    all-gather) against the single-GPU step: loss, the gradient rows each rank owns, and the parameters after Adam."""
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
     dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
@@ -145,24 +187,52 @@ def _gpu_worker(rank, world, port, out):
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests'))
     import ssl_test_helpers as H
     from oracle import inputs, replay
+    from sslrec_b200.optim import FusedAdam
     from sslrec_b200.parallel import RowShard
-    g = replay.load_golden('simgcl', 'small')
     case = inputs.make_case('small')
-    res = {}
-    for sharded in (False, 'loss', 'all'):
-        model, _ = H.make_model('simgcl', case, g['hp'], device=f'cuda:{rank}')
-        model.load_state_dict({'user_embeds': case['user_e'], 'item_embeds': case['item_e']})
-        if sharded:
-            model.comm = RowShard(dist, rank, world, case['n_user'] + case['n_item'], shard_propagation=(sharded == 'all'))
-            model._plans.clear()
+    nu, n = case['n_user'], case['n_user'] + case['n_item']
+    for name, gname in (('lightgcn', 'lightgcn'), ('simgcl', 'simgcl'), ('sgl', 'sgl'), ('sgl_nd', 'sgl_nd')):
+        size = 'tiny' if name == 'sgl_nd' else 'small'
+        g = replay.load_golden(gname, size)
+        case = inputs.make_case(size)
+        nu, n = case['n_user'], case['n_user'] + case['n_item']
         batch = [torch.from_numpy(case[k]).cuda() for k in ('ancs', 'poss', 'negs')]
-        loss, _ = model.cal_loss(batch)
-        loss.backward()
-        res[sharded] = (loss.item(), model.user_embeds.grad.clone(), model.item_embeds.grad.clone())
-    for mode in ('loss', 'all'):
-        assert abs(res[mode][0] - res[False][0]) <= 1e-6 * max(1.0, abs(res[False][0])), mode
-        for a, b in zip(res[mode][1:], res[False][1:]):
-            assert torch.allclose(a, b, rtol=1e-4, atol=1e-7 + 1e-5 * b.abs().max().item()), mode
+        res = {}
+        for mode in ('single', 'loss', 'symm', 'nccl'):
+            model, _ = H.make_model(name.split('_')[0], case, g['hp'], device=f'cuda:{rank}')
+            model.load_state_dict({'user_embeds': case['user_e'], 'item_embeds': case['item_e']})
+            comm = None
+            if mode != 'single':
+                comm = RowShard(dist, rank, world, n, n_user=nu, shard_propagation=(mode != 'loss'),
+                                transport='nccl' if mode == 'nccl' else 'auto')
+                model.shard_to(comm)
+            opt = FusedAdam(model.parameters(), lr=1e-2, row_shards=getattr(model, 'row_shards', None), comm=comm)
+            losses = []
+            for step in range(2):                        # the second step re-uses every shared table
+                opt.zero_grad()
+                loss, _ = model.cal_loss(batch)
+                loss.backward()
+                if step == 0:
+                    grads = torch.cat([model.user_embeds.grad, model.item_embeds.grad]).clone()
+                opt.step()
+                losses.append(loss.item())
+            torch.cuda.synchronize()
+            res[mode] = (losses, grads, torch.cat([model.user_embeds.detach(), model.item_embeds.detach()]).clone(), comm)
+        ref = res['single']
+        for mode in ('loss', 'symm', 'nccl'):
+            losses, grads, params, comm = res[mode]
+            for a, b in zip(losses, ref[0]):
+                assert abs(a - b) <= 2e-6 * max(1.0, abs(b)), (name, mode, losses, ref[0])
+            rows = torch.arange(n, device=grads.device)
+            if mode != 'loss':                           # sharded propagation: a rank computes the gradient rows it owns
+                (u0, u1), (i0, i1) = comm.ranges
+                rows = torch.cat([rows[u0:u1], rows[i0:i1]])
+            tol = 1e-7 + 2e-5 * ref[1].abs().max().item()
+            assert torch.allclose(grads[rows], ref[1][rows], rtol=1e-4, atol=tol), (name, mode)
+            assert torch.allclose(params, ref[2], rtol=1e-4, atol=2e-5), (name, mode)       # two Adam steps at lr 1e-2
+            twin = params.clone()
+            dist.broadcast(twin, src=0)
+            assert torch.equal(params, twin), (name, mode, 'replicas diverged')
     dist.destroy_process_group()
 
 
