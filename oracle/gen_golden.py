@@ -41,12 +41,16 @@ MODEL_HP = {
     'sgl_nd': dict(layer_num=2, keep_rate=0.5, augmentation='node_drop'),
     'ncl': dict(layer_num=3, high_order=2, cluster_num=5),
     'hccf': dict(layer_num=2, keep_rate=0.5, hyper_num=16, leaky=0.5),
+    # the YAML sizes of the proto / hyper contrastive models (ncl.yml: cluster_num 50; hccf.yml: hyper_num 128)
+    'ncl_k50': dict(layer_num=3, high_order=2, cluster_num=50),
+    'hccf_h128': dict(layer_num=2, keep_rate=0.5, hyper_num=128, leaky=0.5),
     'directau': dict(layer_num=2, gamma=2.0),
     'lightgcl': dict(layer_num=2, dropout=0, cl_weight=0.1, reg_weight=1.0e-6, temp=0.1, svd_q=5),
 }
 CASES = [('lightgcn', 'tiny'), ('simgcl', 'tiny'), ('sgl', 'tiny'), ('sgl_nd', 'tiny'), ('ncl', 'tiny'),
          ('hccf', 'tiny'), ('lightgcn', 'small'), ('simgcl', 'small'), ('sgl', 'small'), ('simgcl', 'mid'),
-         ('directau', 'tiny'), ('directau', 'small'), ('lightgcl', 'tiny'), ('lightgcl', 'small')]
+         ('directau', 'tiny'), ('directau', 'small'), ('lightgcl', 'tiny'), ('lightgcl', 'small'),
+         ('ncl_k50', 'small'), ('hccf_h128', 'small')]
 
 
 def _scratch(case):

@@ -214,10 +214,12 @@ template <int D>
 int launch(const float *R, int64_t n_r, const float *C, const float *C_t, int64_t n_c, int dim, const float *colscale,
            float offset, int n_split, float *rowsum_part, float *o_part, cudaStream_t st) {
     const size_t smem = sizeof(float) * (D * BM + D * BN + BN * D + BN * EPITCH) + 2 * sizeof(uint64_t);
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[64] = {};      // cudaFuncSetAttribute is per device
+    int dev = 0;
+    SSL_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
         SSL_CUDA(cudaFuncSetAttribute(softmax_gemm_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
+        if (dev >= 0 && dev < 64) configured[dev] = true;
     }
     const int64_t grid = ((n_r + BM - 1) / BM) * n_split;
     softmax_gemm_kernel<D><<<(unsigned)grid, 256, smem, st>>>(R, n_r, C, C_t, n_c, dim, colscale, offset, n_split, rowsum_part, o_part);

@@ -478,10 +478,13 @@ int launch_tc(const float *R_hi, const float *R_lo, int64_t n_r, const float *C_
     constexpr int KCH = D / 32;
     const size_t smem = 1024 + 2 * (size_t)KCH * BM * 128 + (size_t)ST1 * 2 * KCH * BN * 128 + (size_t)ST2 * 2 * (BN / 32) * D * 128 +
                         32 * sizeof(uint64_t) + 16 + 3 * 128 * sizeof(float);
-    static bool configured = false;
-    if (!configured) {
+    // cudaFuncSetAttribute is per DEVICE: remember which devices of this process are configured
+    static bool configured[64] = {};
+    int dev = 0;
+    SSL_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
         SSL_CUDA(cudaFuncSetAttribute(softmax_gemm_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
+        if (dev >= 0 && dev < 64) configured[dev] = true;
     }
     const int64_t grid = ((n_r + BM - 1) / BM) * n_split;
     softmax_gemm_tc_kernel<D><<<(unsigned)grid, kNumThreads, smem, st>>>(mr_hi, mr_lo, mc_hi, mc_lo, mt_hi, mt_lo, n_r, n_c, colscale, offset,

@@ -23,8 +23,11 @@ Exchange steps -- the only inter-GPU traffic on the path:
     backward one all-gather of the [N_side/world, d] dense table-gradient blocks.
 Propagation is sharded only when ``shard_propagation`` (automatic by table size): for the bundled-dataset
 shapes a layer takes ~0.15 ms while its all-gather would move the whole 123 MB layer, so there the SpMM is
-replicated and only the loss is sharded.  BPR on the replicated batch and the regulariser are rank-local
-and bit-identical across ranks.
+replicated and only the loss is sharded.  With sharded propagation every parameter row has ONE owner that
+computes its update and stores it into all replicas, so the replicas are bit-identical by construction; with
+loss-only sharding every rank repeats the same propagation / BPR / Adam arithmetic, and because the BPR backward
+adds batch rows with floating-point atomics the replicas agree to fp32 rounding (call ``RowShard.resync(params)``
+-- a broadcast from rank 0 -- once per epoch if exact agreement matters).
 
 ``BatchShard`` is the other way to use N GPUs: the batches are the sharded unit.  Every rank runs the
 whole step on its OWN batch of B samples and the only exchange is one all-reduce (average) of the
@@ -149,6 +152,11 @@ class RowShard:
             self._barrier_handle.barrier(channel=0)
         else:
             self.dist.barrier()
+
+    def resync(self, params) -> None:
+        """Broadcast rank 0's parameters (loss-only sharding: removes the rounding-level drift between replicas)."""
+        for p in params:
+            self.dist.broadcast(p.data, src=0)
 
     # ---- loss sharding (InfoNCE table rows) -------------------------------------------------------
     def allreduce_sum(self, t: torch.Tensor) -> torch.Tensor:

@@ -113,7 +113,7 @@ def test_masked_spmm_is_adjoint_of_its_transpose(mode):
     kept = apply(ones, False)[:, 0].double().sum().item() / (2.0 * float(adj.vals.astype(np.float64).sum()))
     assert abs(kept - keep) < 0.02
     if mode == 'injected':
-        ref = torch.spmm(O.edged(adj, m) if False else O.edge_dropped(adj, m.cpu().numpy().astype(bool), keep, True, torch.float64), x.cpu().double())
+        ref = torch.spmm(O.edge_dropped(adj, m.cpu().numpy().astype(bool), keep, True, torch.float64), x.cpu().double())
         H.close(ax, ref, 1e-5, 1e-6, 'injected-mask SpMM')
 
 

@@ -14,7 +14,8 @@ pytestmark = pytest.mark.gpu
 
 CASES = [('lightgcn', 'tiny'), ('simgcl', 'tiny'), ('sgl', 'tiny'), ('sgl_nd', 'tiny'), ('ncl', 'tiny'), ('hccf', 'tiny'),
          ('lightgcn', 'small'), ('simgcl', 'small'), ('sgl', 'small'), ('simgcl', 'mid'),
-         ('directau', 'tiny'), ('directau', 'small'), ('lightgcl', 'tiny'), ('lightgcl', 'small')]
+         ('directau', 'tiny'), ('directau', 'small'), ('lightgcl', 'tiny'), ('lightgcl', 'small'),
+         ('ncl_k50', 'small'), ('hccf_h128', 'small')]        # the YAML sizes: ncl.yml cluster_num 50, hccf.yml hyper_num 128
 
 
 def _run(model_key, case_name):
@@ -38,13 +39,13 @@ def _run(model_key, case_name):
             assert np.array_equal(r[o], g['lgcl_rows'][og]) and np.array_equal(c[o], g['lgcl_cols'][og])
             assert np.array_equal(v[o].view(np.uint32), g['lgcl_vals'][og].view(np.uint32))
     model.load_state_dict(sd)
-    if model_key == 'ncl':
+    if model_key.split('_')[0] == 'ncl':
         model.user_centroids = torch.from_numpy(g['user_centroids']).cuda()
         model.item_centroids = torch.from_numpy(g['item_centroids']).cuda()
         model.user2cluster = torch.from_numpy(g['user2cluster']).cuda()
         model.item2cluster = torch.from_numpy(g['item2cluster']).cuda()
     batch = [torch.from_numpy(case[k]).cuda() for k in ('ancs', 'poss', 'negs')]
-    if model_key == 'ncl':
+    if model_key.split('_')[0] == 'ncl':
         batch.append(torch.zeros(case['batch'], dtype=torch.int64).cuda())
     return g, case, model, batch
 

@@ -11,7 +11,8 @@ from oracle import inputs, replay
 
 CASES = [('lightgcn', 'tiny'), ('simgcl', 'tiny'), ('sgl', 'tiny'), ('sgl_nd', 'tiny'), ('ncl', 'tiny'),
          ('hccf', 'tiny'), ('lightgcn', 'small'), ('simgcl', 'small'), ('sgl', 'small'), ('simgcl', 'mid'),
-         ('directau', 'tiny'), ('directau', 'small'), ('lightgcl', 'tiny'), ('lightgcl', 'small')]
+         ('directau', 'tiny'), ('directau', 'small'), ('lightgcl', 'tiny'), ('lightgcl', 'small'),
+         ('ncl_k50', 'small'), ('hccf_h128', 'small')]        # the YAML sizes: ncl.yml cluster_num 50, hccf.yml hyper_num 128
 
 
 def _close(a, b, rtol, atol, what):
