@@ -291,6 +291,33 @@ SSL_API int ssl_unit_rows_bwd(const float *xhat, const float *rinv, const int64_
                       void *stream);
 
 /* ------------------------------------------------------------------------------------------
+ * a7  HCCF's hyper-graph branch (hccf.py:43-49 + HGNNLayer :100-108) and its autograd backward without library GEMMs.
+ * All products are skinny (n rows x {dim, hyper_num} <= 128), so two kernel shapes cover them:
+ * ssl_rowgemm   out[r, :n_out] (+)= leaky( scale * ( in1[r, :k1] M1 + in2[r, :k2] M2 ), slope )     row-local
+ *     M1 [k1, n_out] row-major (m1_trans: given as [n_out, k1]); the second product is optional (in2 = NULL);
+ *     pre_ref: in1[r, j] is multiplied by act'(pre_ref[r, j]) = (pre_ref > 0 ? 1 : pre_slope) while it is loaded
+ *     (dZ = dY * act'(Y): LeakyReLU keeps the sign, so the saved OUTPUT tells the derivative); slope = 1: no activation.
+ *     replaces  E_side @ W * mult (:43-44), adj @ hids (:106) and, in the backward, dZ @ lat^T + X @ dlat^T, H @ dlat, dA @ W^T.
+ * ssl_colgemm   out[k1, k2] = post( scale * sum_r in1[r, :k1]^T (x) in2[r, :k2] )                   reduction over rows
+ *     per-CTA partials part[ssl_colgemm_parts(n_rows), k1, k2] are reduced in a fixed order (bit-reproducible);
+ *     pre_ref acts on in2 as above; mode 0: out_act (optional) = leaky(out); mode 1: out *= act'(ref).
+ *     replaces  adj.T @ embeds (:105) and, in the backward, H^T dZ and E^T dA.
+ * ssl_hyper_dropout  F.dropout(A, p = 1 - keep) (:48-49): out = x * m / keep (accumulate: out += ..., the backward);
+ *     mode 1: m = floor(U + keep) from the in-kernel counter-based generator keyed (seed, stream_id; row, 4-column group);
+ *     mode 2: m = mask [n, h] fp32 of 0 / 1 (injected draws).
+ * ------------------------------------------------------------------------------------------ */
+SSL_API int ssl_rowgemm(const float *in1, int64_t in1_stride, int32_t k1, const float *m1, int32_t m1_trans, const float *in2,
+                int64_t in2_stride, int32_t k2, const float *m2, int32_t m2_trans, const float *pre_ref, int64_t pre_stride,
+                float pre_slope, float *out, int64_t out_stride, int32_t n_out, float scale, float slope, int32_t accumulate, int64_t n_rows,
+                void *stream);
+SSL_API int ssl_colgemm_parts(int64_t n_rows);
+SSL_API int ssl_colgemm(const float *in1, int64_t in1_stride, int32_t k1, const float *in2, int64_t in2_stride, int32_t k2,
+                const float *pre_ref, int64_t pre_stride, float slope, int64_t n_rows, float *part, float scale, int32_t mode,
+                const float *ref, float *out, float *out_act, void *stream);
+SSL_API int ssl_hyper_dropout(const float *x, float *out, int64_t n, int32_t h, float keep, int32_t mode, const float *mask, uint64_t seed,
+                      uint32_t stream_id, int32_t accumulate, void *stream);
+
+/* ------------------------------------------------------------------------------------------
  * a17  KMeansClustering (aug_utils.py:142-157, NCL): one Lloyd iteration = assignment
  *   idx[r] = argmin_k sum_j (x_rj - c_kj)^2 (ties -> lowest k) and the centroid update
  *   c_k = sum_{idx[r]=k} x_r / (count_k + 1e-6), in place.  Deterministic (static row partition,

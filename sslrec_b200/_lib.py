@@ -77,6 +77,10 @@ def _load():
         'ssl_axpy': (C.c_int, [vp, vp, i64, vp, f32, vp]),
         'ssl_adam_step': (C.c_int, [vp, vp, vp, vp, i64, i64, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, vp]),
         'ssl_adam_step_peers': (C.c_int, [vp, C.POINTER(vp), i32, vp, vp, vp, i64, i64, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, vp]),
+        'ssl_rowgemm': (C.c_int, [vp, i64, i32, vp, i32, vp, i64, i32, vp, i32, vp, i64, f32, vp, i64, i32, f32, f32, i32, i64, vp]),
+        'ssl_colgemm_parts': (C.c_int, [i64]),
+        'ssl_colgemm': (C.c_int, [vp, i64, i32, vp, i64, i32, vp, i64, f32, i64, vp, f32, i32, vp, vp, vp, vp]),
+        'ssl_hyper_dropout': (C.c_int, [vp, vp, i64, i32, f32, i32, vp, C.c_uint64, C.c_uint32, i32, vp]),
         'ssl_predict_mask': (C.c_int, [vp, i64, vp, i64, vp, i64, i64, i32, vp, vp, vp, vp, vp]),
         'ssl_topk': (C.c_int, [vp, i64, i64, i32, vp, vp, vp]),
         'ssl_align_fwd': (C.c_int, [vp, vp, i64, i32, vp, vp]),

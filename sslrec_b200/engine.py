@@ -1059,6 +1059,129 @@ def dense_infonce_spec_nodes_mean(embeds1, embeds2, nodes, temp):
     return _DenseInfoNceFn.apply(embeds1, embeds2, embeds2, nodes, nodes, float(temp), 1, True, 1e-8, True)
 
 
+# ---- HCCF's hyper-graph branch (hccf.py:43-49, HGNNLayer :100-108) on the library's skinny-GEMM kernels ---------------------
+
+def _rowgemm(in1, k1, m1, m1_trans, out, n_out, scale=1.0, slope=1.0, accumulate=False, in2=None, k2=0, m2=None, m2_trans=False, pre_ref=None,
+             pre_slope=1.0):
+    """out[r, :n_out] (+)= leaky(scale * (in1[r, :k1] M1 + in2[r, :k2] M2)); 2-D row-strided views are fine."""
+    with torch.cuda.device(out.device):
+        check(lib.ssl_rowgemm(in1.data_ptr(), in1.stride(0), k1, m1.data_ptr(), int(m1_trans), _ptr(in2), 0 if in2 is None else in2.stride(0), k2,
+                              _ptr(m2), int(m2_trans), _ptr(pre_ref), 0 if pre_ref is None else pre_ref.stride(0), pre_slope, out.data_ptr(), out.stride(0),
+                              n_out, scale, slope, int(accumulate), out.shape[0], _stream(out)), 'ssl_rowgemm')
+
+
+def _colgemm(in1, k1, in2, k2, scale=1.0, slope=1.0, pre_ref=None, mode=0, ref=None, want_act=False):
+    """out [k1, k2] = post(scale * sum_r in1[r]^T (x) in2[r]) (+ leaky(out) when want_act); deterministic two-stage reduction."""
+    n = in1.shape[0]
+    f = dict(device=in1.device, dtype=torch.float32)
+    part = torch.empty(int(lib.ssl_colgemm_parts(n)), k1, k2, **f)
+    out = torch.empty(k1, k2, **f)
+    act = torch.empty(k1, k2, **f) if want_act else None
+    with torch.cuda.device(in1.device):
+        check(lib.ssl_colgemm(in1.data_ptr(), in1.stride(0), k1, in2.data_ptr(), in2.stride(0), k2, _ptr(pre_ref), 0 if pre_ref is None else pre_ref.stride(0),
+                              slope, n, part.data_ptr(), scale, mode, _ptr(ref), out.data_ptr(), _ptr(act), _stream(in1)), 'ssl_colgemm')
+    return (out, act) if want_act else out
+
+
+class _IncidenceFn(torch.autograd.Function):
+    """A = E_side W mult (hccf.py:43-44): [n, d] x [d, H]."""
+
+    @staticmethod
+    def forward(ctx, e, w, mult):
+        _require_cuda(e, 'embeddings')
+        e_, w_ = e.detach(), w.detach().contiguous()
+        if e_.stride(1) != 1:
+            e_ = e_.contiguous()
+        a = torch.empty(e_.shape[0], w_.shape[1], device=e_.device, dtype=torch.float32)
+        _rowgemm(e_, e_.shape[1], w_, False, a, w_.shape[1], scale=mult)
+        ctx.pack = (e_, w_, mult)
+        return a
+
+    @staticmethod
+    def backward(ctx, ga):
+        e, w, mult = ctx.pack
+        ga = ga.contiguous()
+        de = dw = None
+        if ctx.needs_input_grad[0]:
+            de = torch.empty_like(e, memory_format=torch.contiguous_format)
+            _rowgemm(ga, ga.shape[1], w, True, de, e.shape[1], scale=mult)              # dA W^T mult  (W [d, H] read as [n_out = d, k = H])
+        if ctx.needs_input_grad[1]:
+            dw = _colgemm(e, e.shape[1], ga, ga.shape[1], scale=mult)                     # E^T dA mult
+        return de, dw, None
+
+
+def hyper_incidence(e: torch.Tensor, w: torch.Tensor, mult: float) -> torch.Tensor:
+    return _IncidenceFn.apply(e, w, float(mult))
+
+
+@dataclass
+class HyperDrop:
+    """Dropout of one side's incidence for one layer (hccf.py:48-49): keep probability, and either a seed for the in-kernel
+    generator (stream = layer * 2 + side) or an injected [n, H] float 0 / 1 keep mask."""
+    keep: float = 1.0
+    seed: int = 0
+    stream: int = 0
+    mask: Optional[torch.Tensor] = None
+
+
+def _drop(x: torch.Tensor, d: HyperDrop, out: Optional[torch.Tensor] = None, accumulate: bool = False) -> torch.Tensor:
+    if d.keep == 1.0:
+        if out is None:
+            return x
+        out.add_(x) if accumulate else out.copy_(x)
+        return out
+    out = torch.empty_like(x) if out is None else out
+    mask = None if d.mask is None else d.mask.to(torch.float32).contiguous()
+    with torch.cuda.device(x.device):
+        check(lib.ssl_hyper_dropout(x.data_ptr(), out.data_ptr(), x.shape[0], x.shape[1], d.keep, 2 if mask is not None else 1, _ptr(mask),
+                                    d.seed, d.stream, int(accumulate), _stream(x)), 'ssl_hyper_dropout')
+    return out
+
+
+class _HyperLayerFn(torch.autograd.Function):
+    """Both sides' hyper-graph message of one layer: Y_side = act(H act(H^T X_side)), H = dropout(A_side) (hccf.py:48-49,
+    :100-108).  x is the full [N, d] layer input, a_u / a_i the sides' incidences; the backward returns dX, dA_u, dA_i."""
+
+    @staticmethod
+    def forward(ctx, x, a_u, a_i, slope, drop_u: HyperDrop, drop_i: HyperDrop):
+        _require_cuda(x, 'layer input')
+        x_ = x.detach().contiguous()
+        nu, d = a_u.shape[0], x_.shape[1]
+        y = torch.empty_like(x_)
+        saved = []
+        for a, drop, lo, hi in ((a_u.detach().contiguous(), drop_u, 0, nu), (a_i.detach().contiguous(), drop_i, nu, x_.shape[0])):
+            h = a.shape[1]
+            hk = _drop(a, drop)
+            xs, ys = x_[lo:hi], y[lo:hi]
+            lat, latact = _colgemm(hk, h, xs, d, slope=slope, want_act=True)               # act(H^T X)   (:105)
+            _rowgemm(hk, h, latact, False, ys, d, slope=slope)                               # act(H lat)   (:106)
+            saved.append((hk, lat, latact, drop, lo, hi))
+        ctx.pack = (x_, y, slope, saved)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, y, slope, saved = ctx.pack
+        gy = gy.contiguous()
+        d = x.shape[1]
+        gx = torch.empty_like(x)
+        gas = []
+        for hk, lat, latact, drop, lo, hi in saved:
+            h = hk.shape[1]
+            xs, ys, gs = x[lo:hi], y[lo:hi], gy[lo:hi]
+            # dZ = dY * act'(Y) is formed while dY is loaded;  dlat = (H^T dZ) * act'(lat)
+            dlat = _colgemm(hk, h, gs, d, slope=slope, pre_ref=ys, mode=1, ref=lat)
+            dhk = torch.empty_like(hk)
+            _rowgemm(gs, d, latact, True, dhk, h, in2=xs, k2=d, m2=dlat, m2_trans=True, pre_ref=ys, pre_slope=slope)     # dZ lat^T + X dlat^T
+            _rowgemm(hk, h, dlat, False, gx[lo:hi], d)                                      # dX = H dlat
+            gas.append(_drop(dhk, drop, out=torch.empty_like(dhk)) if drop.keep != 1.0 else dhk)
+        return gx, gas[0], gas[1], None, None, None
+
+
+def hyper_layer(x, a_u, a_i, slope: float, drop_u: HyperDrop, drop_i: HyperDrop) -> torch.Tensor:
+    return _HyperLayerFn.apply(x, a_u, a_i, float(slope), drop_u, drop_i)
+
+
 class _SumSqFn(torch.autograd.Function):
     """reg_params over the flat table: value by a deterministic reduction; the gradient 2 g W is
     added into the state's G_e0 sink (consumed by the last backward layer's epilogue)."""

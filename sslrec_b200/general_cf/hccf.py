@@ -1,12 +1,12 @@
 """HCCF -- drop-in for models/general_cf/hccf.py.  The GCN half of every layer is the sm_100a SpMM
 with a fresh, rescaled in-kernel edge mask (hccf.py:33,47); the two contrastive terms per layer and
 side run through the fused InfoNCE kernels (loss_utils.py:42-51); the hyper-graph half
-(E W, H^T E, H . : dense [N_side, d] x [d, hyper_num] products, hccf.py:43-49,100-108) are plain
-library GEMMs left to cuBLAS through torch, tied together by torch autograd."""
+(E W, H^T X, H . : skinny [N_side, d] x [d, hyper_num] products with dropout and LeakyReLU, hccf.py:43-49,100-108)
+and its backward run on the library's row-local / row-reducing kernels (csrc/hyper.cu: no cuBLAS, the dropout mask is
+drawn in-kernel).  torch autograd only orders the nodes."""
 from __future__ import annotations
 
 import torch
-import torch.nn.functional as F
 from torch import nn
 
 from .. import engine as E
@@ -42,32 +42,29 @@ class HCCF(BaseModel):
     def _gcn_layer(self, embeds, view, layer):
         return E.spmm(self._plan(), embeds, view, layer)
 
-    def _dropout(self, x, keep_rate, layer, side):
+    def _hyper_drop(self, keep_rate, layer, side, seed) -> E.HyperDrop:
+        """The dropout of one side's incidence at one layer (hccf.py:48-49): an in-kernel draw keyed by the step's seed and
+        (layer, side), or the injected Bernoulli keeps of the parity tests."""
         if keep_rate == 1.0:
-            return x
+            return E.HyperDrop()
+        mask = None
         if self._inject is not None and 'hyper_keeps' in self._inject:
-            keep = self._inject['hyper_keeps'][layer][side]
-            return x * keep.to(x.dtype) / keep_rate
-        return F.dropout(x, p=1 - keep_rate)
-
-    def _hyper_branch(self, table, incidence, keep_rate, k):
-        """Both sides' hyper-graph message of layer k + 1 (hccf.py:48-49): act(H act(H^T X_side)) with a fresh dropout of H."""
-        nu = self.user_num
-        sides = (table[:nu], table[nu:])
-        out = [self.hgnn_layer(self._dropout(h, keep_rate, k, side), x) for side, (h, x) in enumerate(zip(incidence, sides))]
-        return torch.concat(out, dim=0)
+            mask = self._inject['hyper_keeps'][layer][side]
+        return E.HyperDrop(keep=float(keep_rate), seed=seed, stream=2 * layer + side, mask=mask)
 
     def forward(self, adj, keep_rate):
         """-> (sum over layers [N, d], per-layer SpMM outputs, per-layer hyper outputs)   (hccf.py:38-54)."""
-        incidence = (self.user_embeds @ self.user_hyper_embeds * self.mult,                    # H_user, H_item (:43-44)
-                     self.item_embeds @ self.item_hyper_embeds * self.mult)
+        a_u = E.hyper_incidence(self.user_embeds, self.user_hyper_embeds, self.mult)          # H_user, H_item (:43-44)
+        a_i = E.hyper_incidence(self.item_embeds, self.item_hyper_embeds, self.mult)
         inj = None if self._inject is None else self._inject.get('edge_masks_per_layer')
         view = self.edge_drop.view(keep_rate, self._seeds.next(), per_layer=True, injected=inj)   # a fresh rescaled mask per layer (:47)
+        drop_seed = self._seeds.next()
         layers = [torch.concat([self.user_embeds, self.item_embeds], dim=0)]
         gcn_out, hyper_out = [], []
         for k in range(self.layer_num):
             gcn_out.append(self._gcn_layer(layers[-1], view, k + 1))
-            hyper_out.append(self._hyper_branch(layers[-1], incidence, keep_rate, k))
+            hyper_out.append(E.hyper_layer(layers[-1], a_u, a_i, self.hgnn_layer.slope,                # :48-49
+                                           self._hyper_drop(keep_rate, k, 0, drop_seed), self._hyper_drop(keep_rate, k, 1, drop_seed)))
             layers.append(gcn_out[-1] + hyper_out[-1])                                         # :52
         return sum(layers), gcn_out, hyper_out
 
@@ -99,10 +96,16 @@ class HCCF(BaseModel):
 
 
 class HGNNLayer(nn.Module):
+    """hccf.py:100-108: act(adj @ act(adj.T @ embeds)); the drop-in model calls engine.hyper_layer for both sides at once; this
+    module keeps the activation's slope and serves stand-alone callers through the same kernels (one side)."""
+
     def __init__(self, leaky):
         super().__init__()
+        self.slope = float(leaky)
         self.act = nn.LeakyReLU(negative_slope=leaky)
 
     def forward(self, adj, embeds):
-        hids = self.act(adj.T @ embeds)
-        return self.act(adj @ hids)
+        n = adj.shape[0]
+        empty = adj.new_zeros((0, adj.shape[1]))
+        x = embeds if embeds.is_contiguous() else embeds.contiguous()
+        return E.hyper_layer(torch.cat([x, x.new_zeros((0, x.shape[1]))]), adj, empty, self.slope, E.HyperDrop(), E.HyperDrop())[:n]

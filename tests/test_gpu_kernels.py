@@ -432,3 +432,56 @@ def test_dense_logsumexp_mean_forward_backward(dim, B, n, use_tc, monkeypatch):
     w2.backward()
     assert abs(o2.item() - w2.item()) <= 1e-5 * max(1.0, abs(w2.item()))
     H.close(big.grad, b64.grad, 2e-4, 2e-5 * b64.grad.abs().max().item(), 'grad through slices')
+
+
+@pytest.mark.parametrize('nu,ni,d,h,slope,keep', [(700, 500, 64, 128, 0.5, 0.5), (130, 65, 32, 16, 0.2, 1.0), (1000, 3, 48, 40, 1.0, 0.7),
+                                                  (64, 64, 128, 128, 0.5, 0.5)])
+def test_hyper_branch_forward_backward(nu, ni, d, h, slope, keep):
+    """HCCF's hyper-graph layer (hccf.py:43-49, :100-108) on ssl_rowgemm / ssl_colgemm / ssl_hyper_dropout against torch
+    autograd in float64, with the dropout keeps injected."""
+    from sslrec_b200 import engine as E
+    g = torch.Generator().manual_seed(nu + d + h)
+    eu, ei = torch.randn(nu, d, generator=g) * 0.3, torch.randn(ni, d, generator=g) * 0.3
+    wu, wi = torch.randn(d, h, generator=g) * 0.2, torch.randn(d, h, generator=g) * 0.2
+    x = torch.randn(nu + ni, d, generator=g) * 0.5
+    ku, ki = (torch.rand(nu, h, generator=g) + keep).floor(), (torch.rand(ni, h, generator=g) + keep).floor()
+    gy = torch.randn(nu + ni, d, generator=g)
+    mult = 1.3
+
+    def run(dtype, dev, native):
+        leaves = [t.to(dev, dtype).clone().requires_grad_(True) for t in (eu, ei, wu, wi, x)]
+        e_u, e_i, w_u, w_i, xx = leaves
+        if native:
+            a_u, a_i = E.hyper_incidence(e_u, w_u, mult), E.hyper_incidence(e_i, w_i, mult)
+            du = E.HyperDrop(keep=keep, mask=ku.to(dev)) if keep != 1.0 else E.HyperDrop()
+            di = E.HyperDrop(keep=keep, mask=ki.to(dev)) if keep != 1.0 else E.HyperDrop()
+            y = E.hyper_layer(xx, a_u, a_i, slope, du, di)
+        else:
+            outs = []
+            for e_, w_, k_, xs in ((e_u, w_u, ku, xx[:nu]), (e_i, w_i, ki, xx[nu:])):
+                hk = e_ @ w_ * mult * k_.to(dev, dtype) / keep
+                outs.append(F.leaky_relu(hk @ F.leaky_relu(hk.T @ xs, slope), slope))
+            y = torch.cat(outs)
+        y.backward(gy.to(dev, dtype))
+        return [y.detach()] + [t.grad for t in leaves]
+    import torch.nn.functional as F
+    got = run(torch.float32, 'cuda', True)
+    want = run(torch.float64, 'cpu', False)
+    for name, a, b in zip(('y', 'dE_u', 'dE_i', 'dW_u', 'dW_i', 'dX'), got, want):
+        H.close(a, b, 2e-4, 2e-5 * b.abs().max().item() + 1e-9, f'hyper {name} ({nu},{ni},{d},{h})')
+
+
+def test_hyper_dropout_rng_keep_fraction_and_determinism():
+    from sslrec_b200 import engine as E
+    a = torch.ones(5000, 128, device='cuda')
+    d = E.HyperDrop(keep=0.3, seed=1234, stream=3)
+    o1, o2 = E._drop(a, d), E._drop(a, d)
+    assert torch.equal(o1, o2)                                                     # counter-based: same (seed, stream) -> same mask
+    kept = (o1 != 0).float().mean().item()
+    assert abs(kept - 0.3) < 0.005 and torch.allclose(o1[o1 != 0], torch.tensor(1 / 0.3, device='cuda'))
+    o3 = E._drop(a, E.HyperDrop(keep=0.3, seed=1234, stream=4))
+    assert (o3 != o1).float().mean().item() > 0.3                                   # another (layer, side) stream: another mask
+    # backward = the same mask applied to the gradient
+    gacc = torch.zeros_like(a)
+    E._drop(torch.full_like(a, 2.0), d, out=gacc, accumulate=True)
+    assert torch.equal(gacc, 2.0 * o1)

@@ -41,8 +41,24 @@ def test_hccf_composition_matches_reference_on_cpu(monkeypatch):
     monkeypatch.setattr(model, '_gcn_layer', gcn_layer)
     monkeypatch.setattr(M, 'cal_bpr_loss', O.bpr_loss_sum)
     monkeypatch.setattr(M, 'cal_infonce_loss_spec_nodes', O.infonce_spec_nodes_mean)
+    # the hyper-graph kernels (ssl_rowgemm / ssl_colgemm / ssl_hyper_dropout behind engine.hyper_*) -> torch restatements
+    from sslrec_b200 import engine as E
+    nu = case['n_user']
+    drops = []
+
+    def hyper_layer(x, a_u, a_i, slope, drop_u, drop_i):
+        outs = []
+        for a, drop, xs in ((a_u, drop_u, x[:nu]), (a_i, drop_i, x[nu:])):
+            drops.append(drop)
+            assert drop.keep == hp['keep_rate'] and drop.mask is not None            # the injected Bernoulli keeps reach the kernel call
+            h = a * drop.mask.to(a.dtype) / drop.keep
+            outs.append(O.leaky(h @ O.leaky(h.T @ xs, slope), slope))                    # hccf.py:105-106
+        return torch.cat(outs, 0)
+    monkeypatch.setattr(E, 'hyper_incidence', lambda e, w, mult: e @ w * mult)
+    monkeypatch.setattr(E, 'hyper_layer', hyper_layer)
     batch = [torch.from_numpy(case[k]) for k in ('ancs', 'poss', 'negs')]
     loss, parts = model.cal_loss(batch)
+    assert len(drops) == 2 * hp['layer_num'] and len({(d.stream) for d in drops}) == len(drops)      # one draw per (layer, side)
     assert list(parts) == ['bpr_loss', 'reg_loss', 'cl_loss']
     _close(loss.item(), g['loss'], 2e-6, 1e-7, 'loss')
     for k, v in parts.items():
