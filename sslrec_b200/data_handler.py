@@ -195,8 +195,29 @@ class AllRankTstData(data.Dataset):
 
 
 class DataHandlerGeneralCF:
-    def __init__(self, trn_mat, val_mat=None, tst_mat=None):
-        self._mats = (sp.coo_matrix(trn_mat), val_mat, tst_mat)
+    """``DataHandlerGeneralCF()`` -- no arguments, as the reference builds it (build_data_handler.py) -- loads
+    ./datasets/general_cf/sparse_{yelp,gowalla,amazon}/{train,valid,test}_mat.pkl chosen by ``configs['data']['name']``
+    (data_handler_general_cf.py:11-35); ``DataHandlerGeneralCF(trn_mat, val_mat, tst_mat)`` takes the matrices directly
+    (synthetic graphs, tests)."""
+
+    def __init__(self, trn_mat=None, val_mat=None, tst_mat=None):
+        if trn_mat is None:
+            name = configs['data']['name']
+            if name not in ('yelp', 'gowalla', 'amazon'):
+                raise ValueError(f"data.name '{name}': the general_cf handler knows yelp, gowalla, amazon (data_handler_general_cf.py:12-17)")
+            predir = './datasets/general_cf/sparse_{}/'.format(name)
+            self.trn_file, self.val_file, self.tst_file = predir + 'train_mat.pkl', predir + 'valid_mat.pkl', predir + 'test_mat.pkl'
+            self._mats = None
+        else:
+            self.trn_file = self.val_file = self.tst_file = None
+            self._mats = (sp.coo_matrix(trn_mat), val_mat, tst_mat)
+
+    def _load_one_mat(self, file):
+        """data_handler_general_cf.py:21-35: pickled scipy matrix -> binary float32 COO."""
+        import pickle
+        with open(file, 'rb') as fs:
+            mat = (pickle.load(fs) != 0).astype(np.float32)
+        return sp.coo_matrix(mat)
 
     def _make_torch_adj(self, mat):
         rows, cols, vals, n = normalized_adjacency(mat)
@@ -205,6 +226,8 @@ class DataHandlerGeneralCF:
         return adj.to(configs['device'])
 
     def load_data(self):
+        if self._mats is None:
+            self._mats = (self._load_one_mat(self.trn_file), self._load_one_mat(self.val_file), self._load_one_mat(self.tst_file))
         trn_mat, val_mat, tst_mat = self._mats
         trn_mat = sp.coo_matrix((trn_mat != 0).astype(np.float32))
         self.trn_mat = trn_mat

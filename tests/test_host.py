@@ -2,6 +2,7 @@
 declares, the host logic that needs no GPU (config mirror, data handler, generators, seed streams)."""
 import os
 import re
+import types
 
 import numpy as np
 import pytest
@@ -143,3 +144,57 @@ def test_device_loader_shares_and_flags_with_a_stub_dataset():
     loader = DeviceLoader(ds, 16, seed=4)
     flags = [int(torch.cat([b[3] for b in loader]).sum()) for _ in range(5)]
     assert flags == [1, 1, 0, 1, 0]                                # first sample ever, then pair 0 on every 2nd visit
+
+
+def test_trainer_early_stop_restores_best_state_tests_and_saves(tmp_path, monkeypatch):
+    """Trainer.train (trainer.py:86-137): patience counting on the first metric @ k[0], best state_dict restored into a
+    freshly built model, final evaluate + test, checkpoint under ./checkpoint/{model}/{model}-{data}-{ts}.pth."""
+    import torch
+    from sslrec_b200.config import configs, default_config, load_config
+    from sslrec_b200.trainer import Trainer
+    cfg = default_config('lightgcn')
+    cfg['train'].update(epoch=20, test_step=1, patience=2, save_model=True)
+    cfg['data']['name'] = 'gowalla'
+    load_config(base=cfg, device='cpu')
+    assert configs['train']['early_stop'] is True
+    monkeypatch.chdir(tmp_path)
+
+    class Model(torch.nn.Module):
+        def __init__(self, data_handler=None):
+            super().__init__()
+            self.w = torch.nn.Parameter(torch.zeros(3))
+    scores = [0.10, 0.30, 0.20, 0.25, 0.90]            # best at epoch 1; epochs 2, 3 do not improve -> stop after epoch 3
+    log = []
+    tr = Trainer(types.SimpleNamespace(test_dataloader='tst', valid_dataloader='val'))
+    monkeypatch.setattr(tr, 'create_optimizer', lambda m: None)
+
+    def train_epoch(model, e):
+        with torch.no_grad():
+            model.w.fill_(float(e))
+        log.append(('train', e))
+
+    def evaluate(model, epoch_idx=None, loader=None, data_type=None):
+        log.append(('eval', epoch_idx, data_type, float(model.w[0])))
+        return {'recall': [scores[epoch_idx] if epoch_idx is not None else -1.0], 'ndcg': [0.0]}
+    monkeypatch.setattr(tr, 'train_epoch', train_epoch)
+    monkeypatch.setattr(tr, 'evaluate', evaluate)
+    best = tr.train(Model())
+    assert [x for x in log if x[0] == 'train'] == [('train', e) for e in range(4)]          # stopped by patience, not by epoch count
+    assert float(best.w[0]) == 1.0                                                           # epoch 1's parameters came back
+    assert log[-2][:3] == ('eval', None, None) and log[-2][3] == 1.0                         # final evaluate on the restored model
+    assert log[-1][:3] == ('eval', None, 'Test set')                                         # then test()
+    saved = list((tmp_path / 'checkpoint' / 'lightgcn').glob('lightgcn-gowalla-*.pth'))
+    assert len(saved) == 1 and float(torch.load(saved[0])['w'][0]) == 1.0
+    # without patience: every epoch runs, then test + save
+    cfg2 = default_config('lightgcn')
+    cfg2['train'].update(epoch=3, test_step=2)
+    load_config(base=cfg2, device='cpu')
+    log.clear()
+    tr.train(Model())
+    assert [x[1] for x in log if x[0] == 'train'] == [0, 1, 2] and [x[1] for x in log if x[0] == 'eval'] == [0, 2, None]
+    # unknown metric names are an error, not zeros
+    cfg2['test']['metrics'] = ['recall', 'auc']
+    load_config(base=cfg2, device='cpu')
+    import pytest
+    with pytest.raises(ValueError):
+        Trainer(types.SimpleNamespace(test_dataloader=[])).evaluate(Model())
