@@ -541,17 +541,39 @@ def run_ours(args):
             per_row += row * m['views'] if m['x_out'] else 0
             per_row += (row if m['reduce_views'] else row * m['views']) if m['sum_out'] else 0
             return b + m['rows'] * per_row
+        def prop_min_bytes(m):
+            """Compulsory HBM bytes of the same launch (SURVEY.md 8d bytes_min): every distinct input row ONCE per gathered
+            view (n_cols rows, not nnz), the CSR once, and the same per-row epilogue reads / writes."""
+            row = 4 * m['dim']
+            per_row = 16 + (row * m['views'] if m['residual'] else 0) + sum(row * sv for sv in m['sum_src']) + (row if m['reg_src'] else 0)
+            per_row += row if m.get('reg_src2') else 0
+            per_row += row * m['views'] if m['x_out'] else 0
+            per_row += (row if m['reduce_views'] else row * m['views']) if m['sum_out'] else 0
+            return N * row * m['gather_views'] + 8 * m['nnz'] + m['rows'] * per_row
         prop = [(m, ms) for name, m, ms in launches_all if name in ('prop_fwd', 'prop_bwd')]
         prop_ms = sum(ms for _, ms in prop)
         prop_bytes = sum(prop_alg_bytes(m) for m, _ in prop)
-        achieved = prop_bytes / (prop_ms * 1e-3) / 1e9 if prop else None
+        prop_min = sum(prop_min_bytes(m) for m, _ in prop)
+        secs = prop_ms * 1e-3
+        gather_rate = prop_bytes / secs / 1e9 if prop else None           # counts a gathered row once per stored entry: L2 hits included
+        achieved = prop_min / secs / 1e9 if prop else None                # bytes that MUST cross HBM / time
+        traffic = ncu_traffic('prop_kernel', f'views{views}_dim{d}_{graph}')
+        gpeak = ncu_traffic('gather_peaks', 'l2_resident_GBps')           # measured by tools/gather_bench on this pool (profiles/)
+        n_l = len(prop) if prop else 1
         roofline = {'kernel': 'prop_kernel (ssl_propagate_layer; all forward + transposed-backward launches of the timed steps)',
                     'bound': 'hbm', 'achieved': achieved, 'peak': peaks['hbm_gbs'], 'peak_kind': peak_kind + ' (burst copy)', 'unit': 'GB/s',
-                    'frac': (achieved / peaks['hbm_gbs']) if achieved else None, 'traffic': ncu_traffic('prop_kernel', f'views{views}_dim{d}_{graph}'),
-                    'avg_launch_ms': prop_ms / len(prop) if prop else None, 'alg_bytes_per_launch': prop_bytes / len(prop) if prop else None,
+                    'frac': (achieved / peaks['hbm_gbs']) if achieved else None,
+                    'frac_min': (achieved / peaks['hbm_gbs']) if achieved else None,
+                    'frac_dram': (traffic / (secs / n_l) / 1e9 / peaks['hbm_gbs']) if (traffic and prop) else None,
+                    'traffic': traffic, 'traffic_over_min': (traffic / (prop_min / n_l)) if (traffic and prop) else None,
+                    'min_bytes_per_launch': prop_min / n_l if prop else None,
+                    'l2_inclusive_gather_GBps': gather_rate, 'gather_bytes_per_launch': prop_bytes / n_l if prop else None,
+                    'l2_gather_peak_GBps': gpeak, 'frac_l2_gather': (gather_rate / gpeak) if (gpeak and gather_rate) else None,
+                    'avg_launch_ms': prop_ms / n_l if prop else None,
                     'launches_per_step': len(prop) / K, 'share_of_step': prop_ms / K / prof_ms if prof_ms else None,
-                    'note': 'the 41 MB/view tables of this graph fit the 126 MB L2, so achieved counts L2 hits and can exceed the HBM peak; '
-                            'traffic (ncu dram bytes) is in profiles/'}
+                    'note': 'achieved / frac / frac_min = compulsory bytes (each input row once, CSR once, epilogue rows) over the live CUDA-event time: '
+                            'the HBM roofline; frac_dram = ncu dram bytes of the committed capture over the same time; l2_inclusive_gather_GBps counts a '
+                            'gathered row once per stored entry (what the SMs pull through the L2: bounded by the L2 gather rate, not by HBM)'}
         # the dense InfoNCE contraction (not HBM-bound): on the tcgen05 tensor cores with 3xTF32 error compensation when
         # dim is 32 / 64, else on the FP32 FMA pipe
         nce = [(m, ms) for name, m, ms in launches_all if name in ('nce_gemm_fwd', 'nce_gemm_bwd')]

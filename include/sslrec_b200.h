@@ -93,7 +93,7 @@ SSL_API int ssl_plan_stats(const ssl_plan *plan, int64_t out[4]);
  *   x_v[r]   += eps * sign(x_v[r]) * u / max(|u|_2, 1e-12)                (noise_mode != 0)
  *   x_out[r, v]   = x_v[r]                                                (x_out optional)
  *   sum_out[r, v] = x_v[r] + sum_i sum_src[i][r, v]                       (sum_out optional;
- *                   reduce_views: sum_out[r] = sum_v of the above, + reg_coef * reg_src[r])
+ *                   reduce_views: sum_out[r] = sum_v of the above, + reg_coef * [*reg_coef_dev] * reg_src[r] + reg_src2[r])
  *
  * replaces: t.spmm (lightgcn.py:29, hccf.py:36), the layer sum (lightgcn.py:41, simgcl.py:29,
  * sgl.py:34, ncl.py:41), EdgeDrop (aug_utils.py:18-31) as an in-kernel keep test so no second
@@ -147,6 +147,10 @@ typedef struct ssl_prop_args {
     int32_t n_peers;                  /* 0 on one GPU */
     float *x_out_peers[SSL_MAX_PEERS];    /* peers' copies of the x_out table (same shape, same row addressing) */
     float *sum_out_peers[SSL_MAX_PEERS];  /* peers' copies of the sum_out table */
+    const float *reg_coef_dev;        /* optional device scalar multiplied into reg_coef (the upstream gradient of the
+                                         regulariser term: d loss / d reg_params is only known on the device) */
+    const float *reg_src2;            /* optional second [n_cols, dim] row source added with coefficient 1 (with reduce_views):
+                                         gradient rows that losses wrote for layer 0 (ncl.py:75) */
 } ssl_prop_args;
 
 SSL_API int ssl_propagate_layer(const ssl_plan *plan, const ssl_prop_args *args, void *stream);

@@ -37,6 +37,7 @@ class PropArgs(C.Structure):
         ('noise_eps', C.c_float), ('seed', C.c_uint64 * MAX_VIEWS),
         ('edge_stream_id', C.c_uint32), ('noise_stream_id', C.c_uint32),
         ('n_peers', C.c_int32), ('x_out_peers', vp * MAX_PEERS), ('sum_out_peers', vp * MAX_PEERS),
+        ('reg_coef_dev', vp), ('reg_src2', vp),
     ]
 
 

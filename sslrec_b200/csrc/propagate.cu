@@ -221,7 +221,11 @@ __global__ void __launch_bounds__(kThreads, (V <= 3) ? 4 : 3) prop_kernel(PlanDe
         }
     }
     if (a.sum_out != nullptr && a.reduce_views && lane_on) {
-        if (a.reg_src != nullptr) ssl::fma4(tot, a.reg_coef, ssl::ldg4(a.reg_src + (size_t)grow * dim + col));
+        if (a.reg_src != nullptr) {
+            const float c = (a.reg_coef_dev != nullptr) ? a.reg_coef * __ldg(a.reg_coef_dev) : a.reg_coef;
+            ssl::fma4(tot, c, ssl::ldg4(a.reg_src + (size_t)grow * dim + col));
+        }
+        if (a.reg_src2 != nullptr) ssl::add4(tot, ssl::ldg4(a.reg_src2 + (size_t)grow * dim + col));
         const size_t o = (size_t)grow * dim + col;
         *reinterpret_cast<float4 *>(a.sum_out + o) = tot;
         for (int q = 0; q < a.n_peers; ++q) *reinterpret_cast<float4 *>(a.sum_out_peers[q] + o) = tot;
@@ -394,7 +398,8 @@ extern "C" int ssl_propagate_layer(const ssl_plan *plan, const ssl_prop_args *ar
     SSL_CHECK_ARG(a.x_in != nullptr, "ssl_propagate_layer: x_in is null");
     SSL_CHECK_ARG(a.x_out != nullptr || a.sum_out != nullptr, "ssl_propagate_layer: no output requested");
     SSL_CHECK_ARG(a.n_sum_src >= 0 && a.n_sum_src <= SSL_MAX_SUM_SRC, "ssl_propagate_layer: n_sum_src out of range");
-    SSL_CHECK_ARG(a.reg_src == nullptr || a.reduce_views, "ssl_propagate_layer: reg_src needs reduce_views");
+    SSL_CHECK_ARG((a.reg_src == nullptr && a.reg_src2 == nullptr) || a.reduce_views, "ssl_propagate_layer: reg_src / reg_src2 need reduce_views");
+    SSL_CHECK_ARG(a.reg_coef_dev == nullptr || a.reg_src != nullptr, "ssl_propagate_layer: reg_coef_dev without reg_src");
     bool any_edge = false;
     for (int v = 0; v < a.n_views; ++v) {
         SSL_CHECK_ARG(a.edge_mode[v] >= 0 && a.edge_mode[v] <= 2 && a.noise_mode[v] >= 0 && a.noise_mode[v] <= 2, "ssl_propagate_layer: bad mode for view %d", v);

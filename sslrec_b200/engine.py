@@ -201,6 +201,7 @@ class PropState:
         self._g_sum = None
         self._g_layers: Dict[int, torch.Tensor] = {}
         self._g_e0 = None
+        self.reg_pending: Optional[torch.Tensor] = None     # upstream gradient of sum ||E0||^2 (device scalar), folded into the last backward launch
 
     # ---- sinks -------------------------------------------------------------------------------
     def g_sum(self) -> torch.Tensor:
@@ -290,7 +291,7 @@ class Propagation:
         meta = None
         if TIMER is not None:
             shared = a.in_views == 1 and not any(a.edge_mode[i] for i in range(a.n_views))
-            meta = dict(views=a.n_views, gather_views=1 if shared else a.n_views, dim=a.dim, residual=bool(a.residual),
+            meta = dict(views=a.n_views, gather_views=1 if shared else a.n_views, dim=a.dim, residual=bool(a.residual), reg_src2=bool(a.reg_src2),
                         x_out=bool(a.x_out), sum_out=bool(a.sum_out), reduce_views=bool(a.reduce_views),
                         sum_src=[a.sum_src_views[i] for i in range(a.n_sum_src)], reg_src=bool(a.reg_src),
                         nnz=self.plan.nnz, rows=self.plan.n_rows)
@@ -413,6 +414,12 @@ class Propagation:
         top = L
         while top >= 1 and residual(top) is None:
             top -= 1
+        # regulariser gradient 2 g E0 (loss_utils.py:20-24): read straight from E0 by the last launch's epilogue when that
+        # launch exists (no [N, d] sink to zero, fill and re-read); otherwise materialised into the E0 sink
+        fold_reg = st.reg_pending is not None and not self.any_node and top >= 1
+        if st.reg_pending is not None and not fold_reg:
+            with torch.cuda.device(e0.device):
+                check(lib.ssl_axpy(e0.data_ptr(), st.g_e0().data_ptr(), e0.numel(), st.reg_pending.data_ptr(), 2.0, _stream(e0)), 'ssl_axpy')
         g_e0 = st._g_e0
         if top == 0:
             d0 = residual(0)     # only X_0 got gradient (through the layer sum)
@@ -434,7 +441,10 @@ class Propagation:
             if last and not self.any_node:
                 out = torch.empty(N, d, **opts) if self.comm is None else torch.zeros(N, d, **opts)
                 a.sum_out, a.reduce_views = out.data_ptr(), 1
-                if g_e0 is not None:
+                if fold_reg:
+                    a.reg_src, a.reg_coef, a.reg_coef_dev = e0.data_ptr(), 2.0, st.reg_pending.data_ptr()
+                    a.reg_src2 = _ptr(g_e0)
+                elif g_e0 is not None:
                     a.reg_src, a.reg_coef = g_e0.data_ptr(), 1.0
                 self._launch(a, e0)
                 return out
@@ -1196,11 +1206,10 @@ class _SumSqFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g):
-        st, e0 = ctx.st, ctx.e0
+        st = ctx.st
         g = g.contiguous()
-        sink = st.g_e0()
-        with torch.cuda.device(g.device):
-            check(lib.ssl_axpy(e0.data_ptr(), sink.data_ptr(), e0.numel(), g.data_ptr(), 2.0, _stream(g)), 'ssl_axpy')
+        # the propagation's backward (which autograd runs after this node: it depends on the token) applies 2 g E0
+        st.reg_pending = g if st.reg_pending is None else st.reg_pending + g
         return (None, None) + (torch.zeros((), device=g.device),) * ctx.n_in
 
 

@@ -37,7 +37,8 @@ class W_contrastive(nn.Module):
 class LightGCL(BaseModel):
     def __init__(self, data_handler):
         super().__init__(data_handler)
-        train_mat = data_handler._load_one_mat(data_handler.trn_file) if hasattr(data_handler, 'trn_file') else data_handler.trn_mat
+        # lightgcl.py:16 re-reads the training pickle; a handler built from arrays has no file and hands over the matrix it holds
+        train_mat = data_handler._load_one_mat(data_handler.trn_file) if getattr(data_handler, 'trn_file', None) else data_handler.trn_mat
         train_mat = sp.coo_matrix((train_mat != 0).astype(np.float32))
         train_mat.sum_duplicates()
         # lightgcl.py:16-20 in float32 (the pickle is cast at data_handler_general_cf.py:32): R / sqrt(rowD colD)

@@ -114,13 +114,21 @@ def _assert_topk(idx, wi, decidable, what):
     assert frac >= 0.99, f'{what}: only {frac:.4f} of the top-k positions match exactly'
 
 
-def _compare_grads(model, ue, ie, what, rtol=2e-4, atol_rel=5e-6):
+def _compare_grads(model, ue, ie, what, rtol=2e-4, atol_rel=5e-6, kink_frac=0.0, kink_rel=0.0):
+    """Every gradient entry within rtol * |want| + atol_rel * max|want|.  Models with a kink in the forward pass (LeakyReLU at 0
+    in HCCF's hyper branch, like sign(x) in SimGCL) may have a fraction ``kink_frac`` of entries outside it -- an element whose
+    pre-activation lies within fp32 reassociation noise of zero takes the other branch's derivative on one of the two sides --
+    and those must still be within ``kink_rel`` of the largest entry."""
     for name, got, want in (('user', model.user_embeds.grad, ue.grad), ('item', model.item_embeds.grad, ie.grad)):
         got64, want64 = got.double().cpu(), want.double()
         err = (got64 - want64).abs()
         tol = rtol * want64.abs() + atol_rel * want64.abs().max()
         bad = err > tol
-        assert not bad.any(), f'{what} {name} gradient: {int(bad.sum())} of {bad.numel()} entries off, max err {err.max().item():.3e} (largest entry {want64.abs().max().item():.3e})'
+        msg = f'{what} {name} gradient: {int(bad.sum())} of {bad.numel()} entries off, max err {err.max().item():.3e} (largest entry {want64.abs().max().item():.3e})'
+        if bad.any():
+            print(msg)
+        assert bad.float().mean().item() <= kink_frac, msg
+        assert (not bad.any()) or err.max().item() <= kink_rel * want64.abs().max().item(), msg
 
 
 def _topk_check(model, adj, e_final, what, n_users=1024):
@@ -242,7 +250,7 @@ def test_hccf_amazon_shape_h128_matches_oracle():
     assert abs(loss.item() - ref.item()) <= 1e-5 * max(1.0, abs(ref.item())), (loss.item(), ref.item())
     for k in rparts:
         assert abs(float(parts[k].detach()) - float(rparts[k].detach())) <= 1e-5 * max(1.0, abs(float(rparts[k].detach()))), k
-    _compare_grads(model, ps[0], ps[1], 'hccf/amazon', rtol=5e-4, atol_rel=2e-5)
+    _compare_grads(model, ps[0], ps[1], 'hccf/amazon', rtol=5e-4, atol_rel=2e-5, kink_frac=2e-5, kink_rel=2e-2)
     for name, got, want in (('user_hyper', model.user_hyper_embeds.grad, ps[2].grad), ('item_hyper', model.item_hyper_embeds.grad, ps[3].grad)):
         H.close(got, want, 1e-3, 2e-5 * want.abs().max().item(), 'hccf/amazon grad ' + name)
 
