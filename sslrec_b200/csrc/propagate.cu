@@ -47,7 +47,11 @@ namespace {
 constexpr int kMinSeg = 128;       // rows up to this many entries are never split
 constexpr int kThreads = 256;
 constexpr int kPartialStride = SSL_MAX_VIEWS * SSL_MAX_DIM;
-bool g_force_interleaved = false;   // tests / A-B profiling: ssl_set_option("prop_interleaved", 1)
+// thread-mapping / scheduling variants of prop_kernel, switchable for A/B profiling: ssl_set_option("prop_view_major" |
+// "prop_lite" | "prop_persistent", 0 / 1).  Defaults = the fastest measured on B200 (profiles/r02_prop_variants.md).
+bool g_view_major = false;
+bool g_lite = false;
+bool g_persistent = false;
 
 struct PlanDev {
     const int32_t *colidx;
@@ -68,28 +72,24 @@ __device__ __forceinline__ float sgnf(float x) { return (x > 0.f) ? 1.f : ((x < 
 //         epilogue (SimGCL layer 1);  MODE 1: per-view inputs, no edge masks -> V accumulators, ONE weight per entry;
 // MODE 2: per-view edge masks -> V accumulators, V weights per entry.
 // VM (view-major): V is 1 here, the thread serves view blockIdx.y of a.n_views; MODE 1 / 2 only.
-template <int G, int V, int MODE, bool VM>
-__global__ void __launch_bounds__(kThreads, (V <= 3) ? 4 : 3) prop_kernel(PlanDev p, ssl_prop_args a) {
-    constexpr int RPW = 32 / G;
+// LITE: two entries in flight per group instead of four and 6 resident CTAs per SM instead of 4 (more independent
+// item chains per SM at the same number of outstanding row loads).
+template <int G, int V, int MODE, bool VM, bool LITE>
+__device__ __forceinline__ void prop_item(const PlanDev &p, const ssl_prop_args &a, const int64_t item_idx, const int4 it) {
     constexpr bool SHARED = MODE == 0;
     constexpr int NA = SHARED ? 1 : V;
     constexpr int NW = (MODE == 2) ? V : 1;        // distinct weights per entry
-    constexpr int UNR = (NA == 1 && G >= 8) ? 8 : 4;   // entries whose row gathers are in flight together (single-view: 8)
+    constexpr int UNR = LITE ? ((NA == 1 && G >= 8) ? 4 : 2) : ((NA == 1 && G >= 8) ? 8 : 4);   // entries whose row gathers are in flight together
     static_assert(!VM || (V == 1 && MODE != 0), "view-major serves one view per thread");
     const int lane = threadIdx.x & 31;
     const int gl = lane % G;
     const int grp = lane / G;
     const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (grp * G));
-    const int64_t warp = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
-    const int64_t item_idx = warp * RPW + grp;
     const int dim = a.dim;
     const int col = gl * 4;
     const bool lane_on = col < dim;
     const int vbase = VM ? (int)blockIdx.y : 0;    // first (only) view of this thread
     const int nv = VM ? a.n_views : V;             // views interleaved in the row-wise tables
-
-    int4 it = make_int4(-1, 0, 0, -1);
-    if (item_idx < p.n_items) it = p.items[item_idx];
     const int r = it.x;
     const uint32_t grow = (uint32_t)r + ((r < p.split_local) ? p.off_a : p.off_b);    // global row
 
@@ -232,23 +232,68 @@ __global__ void __launch_bounds__(kThreads, (V <= 3) ? 4 : 3) prop_kernel(PlanDe
     }
 }
 
+constexpr int min_ctas(int V, bool lite) { return lite ? ((V <= 3) ? 6 : 4) : ((V <= 3) ? 4 : 3); }
+
+// One work item per group (grid covers the list), or -- PERSISTENT -- a resident grid whose groups stride over the list with
+// the next item's header prefetched: no CTA turnover (10 k CTAs of ~9 us each at the amazon shape) between items.
+template <int G, int V, int MODE, bool VM, bool LITE, bool PERSISTENT>
+__global__ void __launch_bounds__(kThreads, min_ctas(V, LITE)) prop_kernel(PlanDev p, ssl_prop_args a) {
+    constexpr int RPW = 32 / G;
+    const int grp = (threadIdx.x & 31) / G;
+    const int64_t warp = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+    int64_t item_idx = warp * RPW + grp;
+    int4 it = make_int4(-1, 0, 0, -1);
+    if (item_idx < p.n_items) it = p.items[item_idx];
+    if (!PERSISTENT) {
+        prop_item<G, V, MODE, VM, LITE>(p, a, item_idx, it);
+        return;
+    }
+    const int64_t stride = (int64_t)gridDim.x * (kThreads / 32) * RPW;
+    // all groups of a warp run the same number of rounds (the shuffles inside are group-masked, but a warp must stay converged
+    // at the loop level): iterate while ANY item of the warp's round exists
+    const int64_t warp_first = warp * RPW;
+    for (int64_t base = warp_first; base < p.n_items; base += stride) {
+        const int64_t next = item_idx + stride;
+        int4 it_next = make_int4(-1, 0, 0, -1);
+        if (next < p.n_items) it_next = p.items[next];
+        prop_item<G, V, MODE, VM, LITE>(p, a, item_idx, it);
+        item_idx = next;
+        it = it_next;
+    }
+}
+
+template <int G, int V, int MODE, bool VM>
+int launch_variant(const PlanDev &p, const ssl_prop_args &a, int64_t n_items, cudaStream_t st) {
+    constexpr int RPW = 32 / G;
+    const int64_t items_per_block = (int64_t)(kThreads / 32) * RPW;
+    const int64_t need = (n_items + items_per_block - 1) / items_per_block;
+    const unsigned ny = VM ? (unsigned)a.n_views : 1u;
+    const bool lite = g_lite, pers = g_persistent;
+    const int64_t resident = (int64_t)ssl::kNumSM * min_ctas(V, lite) / ny;      // one resident wave (split over the views when view-major)
+    const dim3 grid((unsigned)(pers ? std::min<int64_t>(need, std::max<int64_t>(resident, 1)) : need), ny);
+    if (lite) {
+        if (pers) prop_kernel<G, V, MODE, VM, true, true><<<grid, kThreads, 0, st>>>(p, a);
+        else prop_kernel<G, V, MODE, VM, true, false><<<grid, kThreads, 0, st>>>(p, a);
+    } else {
+        if (pers) prop_kernel<G, V, MODE, VM, false, true><<<grid, kThreads, 0, st>>>(p, a);
+        else prop_kernel<G, V, MODE, VM, false, false><<<grid, kThreads, 0, st>>>(p, a);
+    }
+    SSL_LAUNCH_CHECK("prop_kernel");
+    return SSL_OK;
+}
+
 template <int G, int V>
 int launch_gv(const ssl_plan *plan, const ssl_prop_args &a, int mode, bool view_major, cudaStream_t st) {
     PlanDev p{plan->colidx, plan->vals, plan->rev, plan->items, plan->long_info, plan->counters, plan->partial,
               plan->n_items, plan->n_long, (int32_t)plan->split_local, (uint32_t)plan->off_a, (uint32_t)plan->off_b};
-    constexpr int RPW = 32 / G;
-    const int64_t items_per_block = (int64_t)(kThreads / 32) * RPW;
-    const int64_t grid = (plan->n_items + items_per_block - 1) / items_per_block;
-    if (grid == 0) return SSL_OK;
+    if (plan->n_items == 0) return SSL_OK;
     if (view_major) {
-        const dim3 g((unsigned)grid, (unsigned)a.n_views);
-        if (mode == 1) prop_kernel<G, 1, 1, true><<<g, kThreads, 0, st>>>(p, a);
-        else prop_kernel<G, 1, 2, true><<<g, kThreads, 0, st>>>(p, a);
-    } else if (mode == 0) prop_kernel<G, V, 0, false><<<(unsigned)grid, kThreads, 0, st>>>(p, a);
-    else if (mode == 1) prop_kernel<G, V, 1, false><<<(unsigned)grid, kThreads, 0, st>>>(p, a);
-    else prop_kernel<G, V, 2, false><<<(unsigned)grid, kThreads, 0, st>>>(p, a);
-    SSL_LAUNCH_CHECK("prop_kernel");
-    return SSL_OK;
+        if (mode == 1) return launch_variant<G, 1, 1, true>(p, a, plan->n_items, st);
+        return launch_variant<G, 1, 2, true>(p, a, plan->n_items, st);
+    }
+    if (mode == 0) return launch_variant<G, V, 0, false>(p, a, plan->n_items, st);
+    if (mode == 1) return launch_variant<G, V, 1, false>(p, a, plan->n_items, st);
+    return launch_variant<G, V, 2, false>(p, a, plan->n_items, st);
 }
 
 template <int G>
@@ -365,8 +410,13 @@ extern "C" int ssl_plan_create_ranges(ssl_plan **out, const int32_t *h_rowptr, c
 
 extern "C" int ssl_set_option(const char *name, int64_t value) {
     SSL_CHECK_ARG(name != nullptr, "ssl_set_option: null name");
-    if (std::string(name) == "prop_interleaved") {
-        g_force_interleaved = value != 0;
+    const std::string n(name);
+    if (n == "prop_view_major" || n == "prop_lite" || n == "prop_persistent") {
+        (n == "prop_view_major" ? g_view_major : (n == "prop_lite" ? g_lite : g_persistent)) = value != 0;
+        return SSL_OK;
+    }
+    if (n == "prop_interleaved") {          // round-2a name: 1 = not view-major
+        g_view_major = value == 0;
         return SSL_OK;
     }
     ssl::set_error("ssl_set_option: unknown option '%s'", name);
@@ -418,7 +468,7 @@ extern "C" int ssl_propagate_layer(const ssl_plan *plan, const ssl_prop_args *ar
     SSL_CHECK_ARG(plan->n_cols + (int64_t)1 < ((int64_t)1 << 32), "ssl_propagate_layer: node ids must fit 32 bits");
     const int mode = any_edge ? 2 : ((a.in_views == 1) ? 0 : 1);
     // view-major: per-view inputs (mode 1 / 2 with more than one view) and no cross-view reduction in the epilogue
-    const bool view_major = a.n_views > 1 && !a.reduce_views && (mode == 2 || a.in_views == a.n_views) && !g_force_interleaved;
+    const bool view_major = a.n_views > 1 && !a.reduce_views && (mode == 2 || a.in_views == a.n_views) && g_view_major;
     cudaStream_t st = (cudaStream_t)stream;
     const int quads = a.dim / 4;
     if (quads <= 4) return launch_g<4>(plan, a, mode, view_major, st);

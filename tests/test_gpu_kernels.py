@@ -485,3 +485,79 @@ def test_hyper_dropout_rng_keep_fraction_and_determinism():
     gacc = torch.zeros_like(a)
     E._drop(torch.full_like(a, 2.0), d, out=gacc, accumulate=True)
     assert torch.equal(gacc, 2.0 * o1)
+
+
+@pytest.mark.parametrize('dim,V', [(64, 3), (128, 1)])
+def test_row_sharded_plan_and_peer_stores_on_one_gpu(dim, V):
+    """The kernel side of the fused all-gather without a second GPU: two plans that own complementary (user range, item
+    range) pairs write their rows into one table and into two stand-in "peer" tables (ssl_prop_args.x_out_peers /
+    sum_out_peers) -- together they must reproduce the full plan's layer bit for bit, and rows a plan does not own stay
+    untouched.  Also the view-reduced last backward layer with the folded regulariser and the sharded Adam's peer stores."""
+    from sslrec_b200 import engine as E
+    from sslrec_b200._lib import check, lib
+    from sslrec_b200.graph import GraphPlan
+    adj = _graph(300, 260, 5000, 3, hub=400)
+    nu, n = adj.n_user, adj.n
+    full = _plan(adj)
+    x = torch.randn(n, V, dim, device='cuda')
+    res = torch.randn(n, V, dim, device='cuda')
+    views = [E.ViewSpec(edge_mode=1, keep=0.7, seed=5 + v) for v in range(V)]
+
+    def launch(plan, out_tabs, peers=(), transpose=False, reduce=False, reg=None):
+        prop = E.Propagation(plan, views, 1)
+        a = prop._args(dim, 1, transpose)
+        a.in_views, a.x_in, a.residual = V, x.data_ptr(), res.data_ptr()
+        field, pf = ('sum_out', 'sum_out_peers') if reduce else ('x_out', 'x_out_peers')
+        setattr(a, field, out_tabs.data_ptr())
+        a.reduce_views = int(reduce)
+        if reg is not None:
+            a.reg_src, a.reg_coef, a.reg_coef_dev, a.reg_src2 = reg[0].data_ptr(), 2.0, reg[1].data_ptr(), reg[2].data_ptr()
+        a.n_peers = len(peers)
+        for q, p in enumerate(peers):
+            getattr(a, pf)[q] = p.data_ptr()
+        prop._launch(a, x)
+
+    cuts = ((0, 120), (nu, nu + 100)), ((120, nu), (nu + 100, n))
+    plans = [GraphPlan(adj.rows, adj.cols, adj.vals, n, torch.device('cuda'), row_ranges=c, side_split=nu) for c in cuts]
+    assert sum(p.nnz for p in plans) == full.nnz and sum(p.n_rows for p in plans) == n
+    for transpose in (False, True):
+        want = torch.empty(n, V, dim, device='cuda')
+        launch(full, want, transpose=transpose)
+        own = torch.full((n, V, dim), -7.0, device='cuda')
+        peers = [torch.full((n, V, dim), -7.0, device='cuda') for _ in range(2)]
+        launch(plans[0], own, peers, transpose=transpose)
+        (a0, a1), (b0, b1) = cuts[0]
+        mine = torch.zeros(n, dtype=torch.bool, device='cuda')
+        mine[a0:a1] = True
+        mine[b0:b1] = True
+        for t in [own] + peers:
+            assert torch.equal(t[mine], want[mine]) and (t[~mine] == -7.0).all()
+        launch(plans[1], own, peers, transpose=transpose)
+        for t in [own] + peers:
+            assert torch.equal(t, want)                      # every "GPU" now holds the whole layer, bit-identical to the unsharded launch
+    # last backward layer: reduce over views + 2 g E0 read from the table + a second row source, stored to the peers as well
+    e0, g, src2 = torch.randn(n, dim, device='cuda'), torch.tensor(0.37, device='cuda'), torch.randn(n, dim, device='cuda')
+    want = torch.empty(n, dim, device='cuda')
+    launch(full, want, transpose=True, reduce=True, reg=(e0, g, src2))
+    own, peer = torch.zeros(n, dim, device='cuda'), torch.zeros(n, dim, device='cuda')
+    for p in plans:
+        launch(p, own, [peer], transpose=True, reduce=True, reg=(e0, g, src2))
+    assert torch.equal(own, want) and torch.equal(peer, want)
+    ref = torch.empty(n, dim, device='cuda')
+    launch(full, ref, transpose=True, reduce=True)
+    H.close(want, ref.double() + 2.0 * 0.37 * e0.double() + src2.double(), 1e-5, 1e-5, 'folded regulariser gradient')
+    # sharded Adam: the owned range is updated and stored into the stand-in replicas
+    p = torch.randn(1000, dim, device='cuda')
+    reps, p_old = [p.clone(), p.clone()], p.clone()
+    gr, m, v = torch.randn_like(p), torch.zeros_like(p), torch.zeros_like(p)
+    p_ref, m_ref, v_ref = p.clone(), m.clone(), v.clone()
+    lo, hi = 200, 650
+    off = 4 * lo * dim
+    arr = (C.c_void_p * 2)(*[r.data_ptr() + off for r in reps])
+    s = torch.cuda.current_stream().cuda_stream
+    check(lib.ssl_adam_step_peers(p.data_ptr() + off, arr, 2, gr.data_ptr() + off, m.data_ptr() + off, v.data_ptr() + off, (hi - lo) * dim, 1,
+                                  1e-2, 0.9, 0.999, 1e-8, 0.0, s))
+    check(lib.ssl_adam_step(p_ref.data_ptr(), gr.data_ptr(), m_ref.data_ptr(), v_ref.data_ptr(), p_ref.numel(), 1, 1e-2, 0.9, 0.999, 1e-8, 0.0, s))
+    for t in [p] + reps:
+        assert torch.equal(t[lo:hi], p_ref[lo:hi])                                        # the owned rows: updated everywhere
+        assert torch.equal(t[:lo], p_old[:lo]) and torch.equal(t[hi:], p_old[hi:])         # the others: untouched
