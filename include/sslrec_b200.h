@@ -50,8 +50,11 @@ SSL_API int ssl_version(void);
 SSL_API const char *ssl_last_error(void);
 /* number of kernel launches issued by this library since load (bench.py's gpu_launches) */
 SSL_API int64_t ssl_launch_count(void);
-/* process-wide switches for tests and A/B profiling: "prop_interleaved" = 1 disables the view-major
- * propagation variant (every view of a row is then accumulated by one thread) */
+/* process-wide switches for tests and A/B profiling of the propagation kernel's variants (value 0 / 1):
+ *   "prop_view_major"  grid.y = view, one accumulator per thread (fewer DRAM bytes, more instructions: slower on B200)
+ *   "prop_lite"        2 instead of 4 entries in flight per group, 6 instead of 4 resident CTAs per SM
+ *   "prop_persistent"  one resident wave of CTAs striding over the work list instead of one CTA per 16 items
+ * defaults: the fastest measured combination (profiles/r02_prop_variants.md) */
 SSL_API int ssl_set_option(const char *name, int64_t value);
 
 /* ------------------------------------------------------------------------------------------

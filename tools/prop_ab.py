@@ -42,10 +42,27 @@ def main():
     shapes['fwd SGL (2 RNG edge masks + clean view)'] = (masked, c_)
     e_ = plain._args(d, 1, True); e_.in_views, e_.x_in, e_.sum_out, e_.reduce_views, e_.residual = V, x.data_ptr(), out2.data_ptr(), 1, res.data_ptr()
     shapes['bwd last layer (reduce over views; interleaved only)'] = (plain, e_)
+    # the HBM-bound regime: one GPU's eighth of BASELINE config 4 (1.5 M nodes, 75 M entries, d = 128, one view)
+    if '--xl' in sys.argv:
+        keys = S.bipartite_keys_device(1_250_000, 250_000, 37_500_000, 2023, 1.0, 'cuda')
+        rp, ci, va = S.normalized_csr_device(keys, 1_250_000, 250_000)
+        xplan = GraphPlan.from_csr(rp, ci, va, 1_500_000, side_split=1_250_000)
+        xx = torch.randn(1_500_000, 1, 128, device='cuda') * 0.1
+        xo = torch.empty_like(xx)
+        xp = E.Propagation(xplan, [E.ViewSpec()], 2)
+        xa = xp._args(128, 2, False); xa.in_views, xa.x_in, xa.x_out = 1, xx.data_ptr(), xo.data_ptr()
+        shapes = {'xl-8th fwd (d=128, 1 view, 75 M entries)': (xp, xa)}
+        x, d, V, plan = xx, 128, 1, xplan
     nnz = plan.nnz
+    combos = [('interleaved', 0, 0, 0), ('view-major', 1, 0, 0), ('interleaved+persistent', 0, 0, 1), ('interleaved+lite', 0, 1, 0),
+              ('interleaved+lite+persistent', 0, 1, 1), ('view-major+lite+persistent', 1, 1, 1)]
+    if ncu:
+        combos = [c for c in combos if c[0] in ('interleaved', 'interleaved+persistent', 'interleaved+lite+persistent')]
     for what, (prop, args) in shapes.items():
-        for mode, flag in (('interleaved', 1), ('view-major', 0)):
-            check(lib.ssl_set_option(b'prop_interleaved', flag))
+        for mode, vm, lite, pers in combos:
+            check(lib.ssl_set_option(b'prop_view_major', vm))
+            check(lib.ssl_set_option(b'prop_lite', lite))
+            check(lib.ssl_set_option(b'prop_persistent', pers))
             if ncu:
                 for _ in range(3):
                     prop._launch(args, x)
@@ -61,7 +78,8 @@ def main():
             ms = e0.elapsed_time(e1) / reps
             gather = nnz * (8 + 4 * d * V)
             print(json.dumps({'shape': what, 'mode': mode, 'ms': round(ms, 4), 'gather_TBps': round(gather / ms / 1e9, 2)}), flush=True)
-    check(lib.ssl_set_option(b'prop_interleaved', 0))
+    for o in (b'prop_view_major', b'prop_lite', b'prop_persistent'):
+        check(lib.ssl_set_option(o, 0))
 
 
 main()
