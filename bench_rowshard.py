@@ -157,9 +157,13 @@ def leg(dist, rank, world, dev, steps=5, warmup=2, full=False, baselines=True, l
     log(f'graph {n_user}x{n_item}, {n_edge} edges generated in {t_gen:.1f}s')
     N = n_user + n_item
     rec = {'graph': f'synthetic config-4 family x {scale}/8: |U|={n_user}, |I|={n_item}, nnz={2 * n_edge}, d={DIM}, L={LAYERS}, B={BATCH}, LightGCN (BPR + reg)',
-           'gpus': world, 'graph_gen_s': t_gen, 'partition': 'rows of A and E sharded: each GPU owns 1/N of the user rows and 1/N of the item rows; full tables replicated'}
+           'gpus': world, 'graph_gen_s': t_gen, 'partition': 'rows of A and E sharded: each GPU owns a contiguous block of the user rows and one of the item rows, cut so that every GPU has the same number of stored entries (+4 per row); full tables replicated'}
     if world > 1:
-        comm = RowShard(dist, rank, world, N, n_user=n_user, shard_propagation=True, dim=DIM, views=1)
+        # block boundaries balanced by the rows' cost: stored entries (gathers) + a constant per row (epilogue, output row)
+        from sslrec_b200.parallel import balanced_bounds
+        ub = balanced_bounds(torch.bincount(keys // n_item, minlength=n_user).float() + 4.0, world)
+        ib = balanced_bounds(torch.bincount(keys % n_item, minlength=n_item).float() + 4.0, world)
+        comm = RowShard(dist, rank, world, N, n_user=n_user, shard_propagation=True, dim=DIM, views=1, user_bounds=ub, item_bounds=ib)
         rec['transport'] = comm.transport
         model, opt, handler = _build(keys, n_user, n_item, dev, comm)
         batches = _make_batches(keys, n_item, steps + warmup, dev, 7)
@@ -187,7 +191,13 @@ def leg(dist, rank, world, dev, steps=5, warmup=2, full=False, baselines=True, l
                            'exchange_ms = what is left of the exchange after the launch (cross-GPU barrier; with the nccl transport the all_gather itself); '
                            'nvlink_GBps = bytes this rank stored into its peers per step / (spmm_ms + adam_ms)',
                     'loss': loss, 'steps': steps, 'warmup': warmup})
+        rec['multicast'] = bool(comm._tables and next(iter(comm._tables.values())).mc_ptr)
         del model, opt, handler, batches
+        comm._tables.clear()                                  # the shared tables (6.1 GB each at config 4) go before rank 0's one-GPU baselines
+        comm._barrier_handle = None
+        del comm
+        import gc
+        gc.collect()
         torch.cuda.empty_cache()
     if baselines:
         # rank 0 alone: one GPU on the 1/8 graph (what each GPU of the sharded run owns), and at the full size the whole graph on one GPU

@@ -115,9 +115,10 @@ class BaseModel(nn.Module):
         comm.barrier()
         # what the sharded optimizer needs per parameter: the owned row range and the peers' base addresses of that parameter
         row_bytes = 4 * self.embedding_size
+        targets = [tb.mc_ptr] if tb.mc_ptr else list(tb.peer_ptrs)      # one multicast store (it also rewrites our copy with the same value) or one store per peer
         self.row_shards = {
-            id(self.user_embeds): (comm.u0, comm.u1, [p for p in tb.peer_ptrs]),
-            id(self.item_embeds): (comm.i0 - self.user_num, comm.i1 - self.user_num, [p + self.user_num * row_bytes for p in tb.peer_ptrs]),
+            id(self.user_embeds): (comm.u0, comm.u1, targets, comm.user_bounds),
+            id(self.item_embeds): (comm.i0 - self.user_num, comm.i1 - self.user_num, [p + self.user_num * row_bytes for p in targets], comm.item_bounds),
         }
 
     def _train_csr(self, device):

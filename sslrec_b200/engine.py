@@ -322,7 +322,15 @@ class Propagation:
 
     @staticmethod
     def _set_peers(a: PropArgs, field: str, tb) -> None:
-        if tb is None or not tb.peer_ptrs:
+        """Where the launch stores its rows besides (or instead of) this GPU's table: the multicast address of the shared table
+        when there is one -- the ONLY store target then, the switch delivers the row to every copy including ours -- else
+        the peers' mapped copies."""
+        if tb is None:
+            return
+        if tb.mc_ptr:
+            setattr(a, field[:-len('_peers')], tb.mc_ptr)          # x_out / sum_out = the multicast address
+            return
+        if not tb.peer_ptrs:
             return
         a.n_peers = len(tb.peer_ptrs)
         arr = getattr(a, field)

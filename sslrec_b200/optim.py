@@ -53,7 +53,7 @@ class FusedAdam(torch.optim.Optimizer):
                 with torch.cuda.device(p.device):
                     stream = torch.cuda.current_stream(p.device).cuda_stream
                     if id(p) in self.row_shards:
-                        lo, hi, peers = self.row_shards[id(p)]
+                        lo, hi, peers = self.row_shards[id(p)][:3]
                         w = p.shape[1] if p.dim() > 1 else 1
                         off = 4 * lo * w
                         arr = (C.c_void_p * max(1, len(peers)))(*[q + off for q in peers])
@@ -75,12 +75,8 @@ class FusedAdam(torch.optim.Optimizer):
         if self.comm.transport == 'symm':
             self.comm.barrier()
             return
-        dist, world = self.comm.dist, self.comm.world
         for p in params:
-            lo, hi, _ = self.row_shards[id(p)]
-            blk = (p.shape[0] + world - 1) // world
-            local = torch.zeros((blk,) + tuple(p.shape[1:]), device=p.device, dtype=p.dtype)
-            local[:hi - lo].copy_(p.data[lo:hi])
-            full = torch.empty((world * blk,) + tuple(p.shape[1:]), device=p.device, dtype=p.dtype)
-            dist.all_gather_into_tensor(full, local)
-            p.data.copy_(full[:p.shape[0]])
+            bounds = self.row_shards[id(p)][3] if len(self.row_shards[id(p)]) > 3 else None
+            if bounds is None:
+                raise RuntimeError('sharded parameter without block boundaries (BaseModel.shard_to provides them)')
+            self.comm.gather_blocks(p.data, bounds)

@@ -14,7 +14,9 @@ Exchange steps -- the only inter-GPU traffic on the path:
     every peer's allocation over NVLink), the kernel's epilogue stores each finished row to the same
     row of all peers' tables (``ssl_prop_args.x_out_peers``), so the NVLink traffic overlaps the
     gathers of the rows still being computed; what remains is a cross-GPU barrier on the stream after the
-    launch.  The ``nccl`` transport (fallback, and the gloo CPU tests) all-gathers the owned row
+    launch.  When the allocation has an NVSwitch multicast address (NVLS) the row is stored ONCE, to that address,
+    and the switch replicates it into all copies (the sender's egress drops from (W-1) x to 1 x the block; the bound
+    becomes each GPU's ingress).  The ``nccl`` transport (fallback, and the gloo CPU tests) all-gathers the owned row
     blocks with ``all_gather_into_tensor`` after the launch;
   * the updated parameters: Adam runs on the owned rows only and stores the new values to every peer's
     replica of the table (``ssl_adam_step_peers``) -- the sixth all-gather of a step, fused the same way;
@@ -56,23 +58,47 @@ def block_range(n: int, world: int, rank: int) -> Tuple[int, int]:
     return lo, min(n, lo + blk)
 
 
+def balanced_bounds(weights: torch.Tensor, world: int) -> List[int]:
+    """Cut rows 0..n into ``world`` contiguous blocks of (nearly) equal total weight: [0, b1, ..., n].  With the rows'
+    stored-entry counts as weights every GPU's SpMM does the same number of gathers even when a few hub rows (the Zipf head of
+    the item side) hold a large share of the entries."""
+    n = int(weights.shape[0])
+    if n == 0:
+        return [0] * (world + 1)
+    cum = torch.cumsum(weights.to(torch.float64) + 1e-9, 0)
+    targets = cum[-1] * torch.arange(1, world, dtype=torch.float64, device=cum.device) / world
+    cuts = torch.searchsorted(cum, targets).clamp_(0, n).tolist()
+    b = [0] + [int(c) for c in cuts] + [n]
+    for i in range(1, len(b)):
+        b[i] = max(b[i], b[i - 1])
+    return b
+
+
 class SharedTable:
     """A [N, ...] fp32 table that exists on every rank at the same logical address: ``t`` is this rank's copy,
     ``peer_ptrs`` the device addresses of the OTHER ranks' copies as mapped into this process (empty for the
     nccl transport)."""
 
-    def __init__(self, t: torch.Tensor, peer_ptrs: List[int], handle=None):
+    def __init__(self, t: torch.Tensor, peer_ptrs: List[int], handle=None, mc_ptr: int = 0):
         self.t, self.peer_ptrs, self.handle = t, peer_ptrs, handle
+        self.mc_ptr = mc_ptr          # NVSwitch multicast address of the table (0: unavailable): ONE store reaches every GPU's copy
 
 
 class RowShard:
     def __init__(self, dist, rank: int, world: int, n: int, shard_propagation='auto', dim: int = 64, views: int = 3,
-                 n_user: Optional[int] = None, transport: str = 'auto'):
+                 n_user: Optional[int] = None, transport: str = 'auto', multicast='auto', user_bounds=None, item_bounds=None):
+        """user_bounds / item_bounds: optional block boundaries [0, ..., n_side] (world + 1 entries each, e.g. from
+        ``balanced_bounds`` of the rows' entry counts); default: equal blocks of ceil(n_side / world) rows."""
         self.dist, self.rank, self.world, self.n = dist, rank, world, n
         self.n_user = n if n_user is None else int(n_user)          # None: one side only (a contiguous block of rows)
-        self.u0, self.u1 = block_range(self.n_user, world, rank)
-        i0, i1 = block_range(n - self.n_user, world, rank)
-        self.i0, self.i1 = self.n_user + i0, self.n_user + i1
+        n_item = n - self.n_user
+        self.user_bounds = [block_range(self.n_user, world, r)[0] for r in range(world)] + [self.n_user] if user_bounds is None else [int(b) for b in user_bounds]
+        self.item_bounds = [block_range(n_item, world, r)[0] for r in range(world)] + [n_item] if item_bounds is None else [int(b) for b in item_bounds]
+        for b, total in ((self.user_bounds, self.n_user), (self.item_bounds, n_item)):
+            if len(b) != world + 1 or b[0] != 0 or b[-1] != total or any(b[i] > b[i + 1] for i in range(world)):
+                raise ValueError('block boundaries must be world + 1 ascending values from 0 to the side\'s row count')
+        self.u0, self.u1 = self.user_bounds[rank], self.user_bounds[rank + 1]
+        self.i0, self.i1 = self.n_user + self.item_bounds[rank], self.n_user + self.item_bounds[rank + 1]
         # Row-sharding the propagation costs one all-gather of the whole [N, V, d] layer per layer and
         # direction; it pays when the SpMM is long (HBM-bound tables far beyond L2, BASELINE.json config 4),
         # not when a layer takes ~0.2 ms (the bundled datasets).  The contraction of the contrastive loss
@@ -85,6 +111,12 @@ class RowShard:
         if transport not in ('symm', 'nccl'):
             raise ValueError("transport must be 'symm' (fused NVLink stores) or 'nccl' (all_gather after the launch)")
         self.transport = transport
+        # symm transport: store finished rows through the NVSwitch multicast address when the allocation has one (one store per
+        # row instead of one per peer: the sender's NVLink egress drops by world - 1, the switch replicates); False = plain
+        # per-peer stores.  SSLREC_B200_MULTICAST=0/1 overrides 'auto'.
+        import os
+        env = os.environ.get('SSLREC_B200_MULTICAST')
+        self.multicast = (env != '0') if (multicast == 'auto' and env is not None) else (True if multicast == 'auto' else bool(multicast))
         self._tables: Dict[tuple, SharedTable] = {}
         self._barrier_handle = None
         self.stats = dict(barriers=0, gathers=0, gathered_bytes=0)
@@ -122,7 +154,8 @@ class RowShard:
             ptrs = [int(p) for q, p in enumerate(hdl.buffer_ptrs) if q != self.rank]
             if self._barrier_handle is None:
                 self._barrier_handle = hdl
-            return SharedTable(t, ptrs, hdl)
+            mc = int(getattr(hdl, 'multicast_ptr', 0) or 0) if self.multicast else 0
+            return SharedTable(t, ptrs, hdl, mc)
         return SharedTable(torch.empty(shape, dtype=torch.float32, device=device), [])
 
     def sync_rows(self, tb: SharedTable) -> None:
@@ -133,17 +166,26 @@ class RowShard:
             self.barrier()
             return
         t = tb.t
-        for lo, hi, side_lo, n_side in ((self.u0, self.u1, 0, self.n_user), (self.i0, self.i1, self.n_user, self.n - self.n_user)):
-            if n_side == 0:
-                continue
-            blk = (n_side + self.world - 1) // self.world
-            local = torch.zeros((blk,) + tuple(t.shape[1:]), device=t.device, dtype=t.dtype)
-            local[:hi - lo].copy_(t[lo:hi])
-            full = torch.empty((self.world * blk,) + tuple(t.shape[1:]), device=t.device, dtype=t.dtype)
-            self.dist.all_gather_into_tensor(full, local)
-            t[side_lo:side_lo + n_side].copy_(full[:n_side])
-            self.stats['gathers'] += 1
-            self.stats['gathered_bytes'] += full.numel() * 4
+        for bounds, side_lo in ((self.user_bounds, 0), (self.item_bounds, self.n_user)):
+            self.gather_blocks(t[side_lo:side_lo + bounds[-1]], bounds)
+
+    def gather_blocks(self, side: torch.Tensor, bounds) -> None:
+        """``side``: one side's rows of a table (a view); rank r has written rows [bounds[r], bounds[r+1]).  All-gather the
+        blocks (padded to the largest) and copy every rank's block into place."""
+        if bounds[-1] == 0:
+            return
+        blk = max(bounds[r + 1] - bounds[r] for r in range(self.world))
+        lo, hi = bounds[self.rank], bounds[self.rank + 1]
+        local = torch.zeros((blk,) + tuple(side.shape[1:]), device=side.device, dtype=side.dtype)
+        local[:hi - lo].copy_(side[lo:hi])
+        full = torch.empty((self.world * blk,) + tuple(side.shape[1:]), device=side.device, dtype=side.dtype)
+        self.dist.all_gather_into_tensor(full, local)
+        for r in range(self.world):
+            a, b = bounds[r], bounds[r + 1]
+            if r != self.rank and b > a:
+                side[a:b].copy_(full[r * blk:r * blk + (b - a)])
+        self.stats['gathers'] += 1
+        self.stats['gathered_bytes'] += full.numel() * 4
 
     def barrier(self) -> None:
         """Cross-GPU barrier ordered on the current stream (no host synchronisation with the symm transport)."""

@@ -18,12 +18,18 @@ def _free_port():
     return p
 
 
-def _gloo_worker(rank, world, port, n):
+def _gloo_worker(rank, world, port, n, balanced=False):
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
     dist.init_process_group('gloo', rank=rank, world_size=world)
     from sslrec_b200.parallel import RowShard
     n_user = n // 3
-    sh = RowShard(dist, rank, world, n, n_user=n_user, shard_propagation=True)
+    from sslrec_b200.parallel import balanced_bounds
+    # unequal blocks: boundaries that balance a skewed per-row weight (one hub row holds a third of the weight)
+    w_u, w_i = torch.ones(n_user), torch.ones(n - n_user)
+    w_i[0] = float(n)
+    ub, ib = balanced_bounds(w_u, world), balanced_bounds(w_i, world)
+    assert ub[0] == 0 and ub[-1] == n_user and ib[-1] == n - n_user and ib[1] <= max(1, (n - n_user) // world)      # the hub's block is short
+    sh = RowShard(dist, rank, world, n, n_user=n_user, shard_propagation=True, user_bounds=ub if balanced else None, item_bounds=ib if balanced else None)
     assert sh.transport == 'nccl'            # gloo: collectives after the launch, no peer stores
     # every global row belongs to exactly one rank, and every rank owns rows of both sides
     owned = torch.zeros(n)
@@ -48,7 +54,7 @@ def _gloo_worker(rank, world, port, n):
     want_u, want_i = torch.arange(n_user * 4.0).view(n_user, 4), 100 + torch.arange((n - n_user) * 4.0).view(n - n_user, 4)
     p_u.data[u0:u1] = want_u[u0:u1]
     p_i.data[i0 - n_user:i1 - n_user] = want_i[i0 - n_user:i1 - n_user]
-    opt = FusedAdam([p_u, p_i], row_shards={id(p_u): (u0, u1, []), id(p_i): (i0 - n_user, i1 - n_user, [])}, comm=sh)
+    opt = FusedAdam([p_u, p_i], row_shards={id(p_u): (u0, u1, [], sh.user_bounds), id(p_i): (i0 - n_user, i1 - n_user, [], sh.item_bounds)}, comm=sh)
     opt._after_sharded_step([p_u, p_i])
     assert torch.equal(p_u.data, want_u) and torch.equal(p_i.data, want_i)
     # InfoNCE table sharding: side ranges split without gaps
@@ -72,9 +78,9 @@ def _gloo_worker(rank, world, port, n):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('n', [10, 11, 64])
-def test_row_shard_plumbing_gloo_world2(n):
-    mp.spawn(_gloo_worker, args=(2, _free_port(), n), nprocs=2, join=True)
+@pytest.mark.parametrize('n,balanced', [(10, False), (11, True), (64, False), (64, True)])
+def test_row_shard_plumbing_gloo_world2(n, balanced):
+    mp.spawn(_gloo_worker, args=(2, _free_port(), n, balanced), nprocs=2, join=True)
 
 
 def test_local_csr_of_two_row_ranges():
@@ -210,8 +216,13 @@ def _gpu_worker(rank, world, port, backend):
             model.load_state_dict({'user_embeds': case['user_e'], 'item_embeds': case['item_e']})
             comm = None
             if mode != 'single':
+                ub = ib = None
+                if mode == 'nccl':            # unequal blocks balanced by the rows' entry counts (the other modes: equal blocks)
+                    from sslrec_b200.parallel import balanced_bounds
+                    ub = balanced_bounds(torch.bincount(torch.from_numpy(case['rows']), minlength=nu).float() + 1, world)
+                    ib = balanced_bounds(torch.bincount(torch.from_numpy(case['cols']), minlength=n - nu).float() + 1, world)
                 comm = RowShard(dist, rank, world, n, n_user=nu, shard_propagation=(mode != 'loss'),
-                                transport='nccl' if mode == 'nccl' else 'auto')
+                                transport='nccl' if mode == 'nccl' else 'auto', user_bounds=ub, item_bounds=ib)
                 model.shard_to(comm)
             opt = FusedAdam(model.parameters(), lr=1e-2, row_shards=getattr(model, 'row_shards', None), comm=comm)
             losses = []
