@@ -50,11 +50,9 @@ SSL_API int ssl_version(void);
 SSL_API const char *ssl_last_error(void);
 /* number of kernel launches issued by this library since load (bench.py's gpu_launches) */
 SSL_API int64_t ssl_launch_count(void);
-/* process-wide switches for tests and A/B profiling of the propagation kernel's variants (value 0 / 1):
- *   "prop_view_major"  grid.y = view, one accumulator per thread (fewer DRAM bytes, more instructions: slower on B200)
- *   "prop_lite"        2 instead of 4 entries in flight per group, 6 instead of 4 resident CTAs per SM
- *   "prop_persistent"  one resident wave of CTAs striding over the work list instead of one CTA per 16 items
- * defaults: the fastest measured combination (profiles/r02_prop_variants.md) */
+/* process-wide switches for tests and A/B profiling (value 0 / 1):
+ *   "prop_view_major"  propagation with grid.y = view and one accumulator per thread: DRAM traffic at 1.03x compulsory instead of
+ *                      1.3x, but 25-40 % slower on B200 (profiles/r02_prop_variants.md); default 0 */
 SSL_API int ssl_set_option(const char *name, int64_t value);
 
 /* ------------------------------------------------------------------------------------------

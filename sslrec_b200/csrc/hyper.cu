@@ -33,6 +33,7 @@ struct RowGemmArgs {
     float scale, slope;                          // out = leaky(acc * scale, slope); slope = 1: no activation
     int accumulate;                              // out += instead of out =
     int64_t n_rows;
+    int vec;                                     // inputs allow 16-byte loads
 };
 
 __device__ __forceinline__ float leaky(float x, float slope) { return x > 0.f ? x : x * slope; }
@@ -58,21 +59,46 @@ __global__ void __launch_bounds__(kT) rowgemm_kernel(RowGemmArgs a) {
     }
     const int tc = threadIdx.x % 16, tr = threadIdx.x / 16;       // 16 column groups x 16 row groups (4 rows each)
     const int64_t n_tiles = (a.n_rows + TR - 1) / TR;
+    const bool vec = a.vec != 0;
     for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
         const int64_t r0 = t * TR;
         __syncthreads();
-        for (int i = threadIdx.x; i < TR * a.k1; i += kT) {
-            const int r = i / a.k1, k = i % a.k1;
-            float v = 0.f;
-            if (r0 + r < a.n_rows) {
-                v = __ldg(a.in1 + (r0 + r) * a.in1_stride + k);
-                if (a.pre_ref != nullptr) v *= (__ldg(a.pre_ref + (r0 + r) * a.pre_stride + k) > 0.f) ? 1.f : a.pre_slope;
+        if (vec) {          // 16-byte global loads (rows are 16-byte aligned and k1, k2 multiples of 4)
+            const int q1 = a.k1 >> 2, q2 = a.k2 >> 2;
+            for (int i = threadIdx.x; i < TR * q1; i += kT) {
+                const int r = i / q1, k = (i - r * q1) * 4;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (r0 + r < a.n_rows) {
+                    v = ssl::ldg4(a.in1 + (r0 + r) * a.in1_stride + k);
+                    if (a.pre_ref != nullptr) {
+                        const float4 y = ssl::ldg4(a.pre_ref + (r0 + r) * a.pre_stride + k);
+                        v.x *= (y.x > 0.f) ? 1.f : a.pre_slope; v.y *= (y.y > 0.f) ? 1.f : a.pre_slope;
+                        v.z *= (y.z > 0.f) ? 1.f : a.pre_slope; v.w *= (y.w > 0.f) ? 1.f : a.pre_slope;
+                    }
+                }
+                float *d = s_in + r * ldi + k;
+                d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
             }
-            s_in[r * ldi + k] = v;
-        }
-        for (int i = threadIdx.x; i < TR * a.k2; i += kT) {
-            const int r = i / a.k2, k = i % a.k2;
-            s_in[r * ldi + a.k1 + k] = (r0 + r < a.n_rows) ? __ldg(a.in2 + (r0 + r) * a.in2_stride + k) : 0.f;
+            for (int i = threadIdx.x; i < TR * q2; i += kT) {
+                const int r = i / q2, k = (i - r * q2) * 4;
+                const float4 v = (r0 + r < a.n_rows) ? ssl::ldg4(a.in2 + (r0 + r) * a.in2_stride + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+                float *d = s_in + r * ldi + a.k1 + k;
+                d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+            }
+        } else {
+            for (int i = threadIdx.x; i < TR * a.k1; i += kT) {
+                const int r = i / a.k1, k = i % a.k1;
+                float v = 0.f;
+                if (r0 + r < a.n_rows) {
+                    v = __ldg(a.in1 + (r0 + r) * a.in1_stride + k);
+                    if (a.pre_ref != nullptr) v *= (__ldg(a.pre_ref + (r0 + r) * a.pre_stride + k) > 0.f) ? 1.f : a.pre_slope;
+                }
+                s_in[r * ldi + k] = v;
+            }
+            for (int i = threadIdx.x; i < TR * a.k2; i += kT) {
+                const int r = i / a.k2, k = i % a.k2;
+                s_in[r * ldi + a.k1 + k] = (r0 + r < a.n_rows) ? __ldg(a.in2 + (r0 + r) * a.in2_stride + k) : 0.f;
+            }
         }
         __syncthreads();
         float acc[4][CPT];
@@ -124,6 +150,7 @@ struct ColGemmArgs {
     float slope;
     float *part;                                       // [gridDim.x, k1, k2]
     int64_t n_rows;
+    int vec;                                           // inputs allow 16-byte loads
 };
 
 // thread -> N1 x N2 outputs: k1 = t1 * N1 + i, k2 = t2 * N2 + j (K1 <= 16 * N1, K2 <= 16 * N2; the shared rows are zero-padded)
@@ -147,18 +174,39 @@ __global__ void __launch_bounds__(kT) colgemm_kernel(ColGemmArgs a) {
     for (int64_t t = tlo; t < thi; ++t) {
         const int64_t r0 = t * TR;
         __syncthreads();
-        for (int i = threadIdx.x; i < TR * L1; i += kT) {
-            const int r = i / L1, k = i % L1;
-            s1[i] = (k < K1 && r0 + r < a.n_rows) ? __ldg(a.in1 + (r0 + r) * a.in1_stride + k) : 0.f;
-        }
-        for (int i = threadIdx.x; i < TR * L2; i += kT) {
-            const int r = i / L2, k = i % L2;
-            float v = 0.f;
-            if (k < K2 && r0 + r < a.n_rows) {
-                v = __ldg(a.in2 + (r0 + r) * a.in2_stride + k);
-                if (a.pre_ref != nullptr) v *= (__ldg(a.pre_ref + (r0 + r) * a.pre_stride + k) > 0.f) ? 1.f : a.slope;
+        if (a.vec) {        // 16-byte global loads and shared stores (K1, K2 multiples of 4, rows 16-byte aligned)
+            for (int i = threadIdx.x; i < TR * (L1 / 4); i += kT) {
+                const int r = i / (L1 / 4), k = (i % (L1 / 4)) * 4;
+                const float4 v = (k < K1 && r0 + r < a.n_rows) ? ssl::ldg4(a.in1 + (r0 + r) * a.in1_stride + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+                *reinterpret_cast<float4 *>(s1 + r * L1 + k) = v;
             }
-            s2[i] = v;
+            for (int i = threadIdx.x; i < TR * (L2 / 4); i += kT) {
+                const int r = i / (L2 / 4), k = (i % (L2 / 4)) * 4;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (k < K2 && r0 + r < a.n_rows) {
+                    v = ssl::ldg4(a.in2 + (r0 + r) * a.in2_stride + k);
+                    if (a.pre_ref != nullptr) {
+                        const float4 y = ssl::ldg4(a.pre_ref + (r0 + r) * a.pre_stride + k);
+                        v.x *= (y.x > 0.f) ? 1.f : a.slope; v.y *= (y.y > 0.f) ? 1.f : a.slope;
+                        v.z *= (y.z > 0.f) ? 1.f : a.slope; v.w *= (y.w > 0.f) ? 1.f : a.slope;
+                    }
+                }
+                *reinterpret_cast<float4 *>(s2 + r * L2 + k) = v;
+            }
+        } else {
+            for (int i = threadIdx.x; i < TR * L1; i += kT) {
+                const int r = i / L1, k = i % L1;
+                s1[i] = (k < K1 && r0 + r < a.n_rows) ? __ldg(a.in1 + (r0 + r) * a.in1_stride + k) : 0.f;
+            }
+            for (int i = threadIdx.x; i < TR * L2; i += kT) {
+                const int r = i / L2, k = i % L2;
+                float v = 0.f;
+                if (k < K2 && r0 + r < a.n_rows) {
+                    v = __ldg(a.in2 + (r0 + r) * a.in2_stride + k);
+                    if (a.pre_ref != nullptr) v *= (__ldg(a.pre_ref + (r0 + r) * a.pre_stride + k) > 0.f) ? 1.f : a.slope;
+                }
+                s2[i] = v;
+            }
         }
         __syncthreads();
 #pragma unroll 2
@@ -261,7 +309,7 @@ int launch_rowgemm(const RowGemmArgs &a, cudaStream_t st) {
         if (dev >= 0 && dev < 64) configured[dev] = true;
     }
     const int64_t n_tiles = (a.n_rows + TR - 1) / TR;
-    const int grid = (int)std::min<int64_t>(n_tiles, 2 * ssl::kNumSM);
+    const int grid = (int)std::min<int64_t>(n_tiles, 3 * ssl::kNumSM);
     rowgemm_kernel<CPT><<<grid, kT, smem, st>>>(a);
     SSL_LAUNCH_CHECK("rowgemm_kernel");
     return SSL_OK;
@@ -302,8 +350,10 @@ extern "C" int ssl_rowgemm(const float *in1, int64_t in1_stride, int32_t k1, con
     SSL_CHECK_ARG(ok_dim(k1) && (in2 == nullptr ? true : (ok_dim(k2) && m2 != nullptr)), "ssl_rowgemm: inner sizes out of range (4..128)");
     SSL_CHECK_ARG(ok_dim(n_out), "ssl_rowgemm: n_out %d out of range (4..128)", n_out);
     if (n_rows == 0) return SSL_OK;
+    auto al16 = [](const void *p, int64_t stride) { return p == nullptr || ((reinterpret_cast<uintptr_t>(p) & 15) == 0 && stride % 4 == 0); };
+    const int vec = (k1 % 4 == 0 && (in2 == nullptr || k2 % 4 == 0) && al16(in1, in1_stride) && al16(in2, in2_stride) && al16(pre_ref, pre_stride)) ? 1 : 0;
     RowGemmArgs a{in1, in1_stride, k1, m1, m1_trans, in2, in2_stride, in2 ? k2 : 0, m2, m2_trans, pre_ref, pre_stride, pre_slope, out, out_stride, n_out,
-                  scale, slope, accumulate, n_rows};
+                  scale, slope, accumulate, n_rows, vec};
     cudaStream_t st = (cudaStream_t)stream;
     switch (round_n(n_out)) {
         case 1: return launch_rowgemm<1>(a, st);
@@ -315,7 +365,7 @@ extern "C" int ssl_rowgemm(const float *in1, int64_t in1_stride, int32_t k1, con
 
 extern "C" int ssl_colgemm_parts(int64_t n_rows) {
     const int64_t n_tiles = (n_rows + TR - 1) / TR;
-    return (int)std::max<int64_t>(1, std::min<int64_t>(n_tiles, 2 * ssl::kNumSM));
+    return (int)std::max<int64_t>(1, std::min<int64_t>(n_tiles, 4 * ssl::kNumSM));
 }
 
 extern "C" int ssl_colgemm(const float *in1, int64_t in1_stride, int32_t k1, const float *in2, int64_t in2_stride, int32_t k2,
@@ -325,7 +375,9 @@ extern "C" int ssl_colgemm(const float *in1, int64_t in1_stride, int32_t k1, con
     SSL_CHECK_ARG(ok_dim(k1) && ok_dim(k2), "ssl_colgemm: sizes %d x %d out of range (4..128)", k1, k2);
     SSL_CHECK_ARG(mode == 0 || (mode == 1 && ref != nullptr), "ssl_colgemm: mode 1 needs ref");
     const int grid = ssl_colgemm_parts(n_rows);
-    ColGemmArgs a{in1, in1_stride, k1, in2, in2_stride, k2, pre_ref, pre_stride, slope, part, n_rows};
+    auto al16 = [](const void *p, int64_t stride) { return p == nullptr || ((reinterpret_cast<uintptr_t>(p) & 15) == 0 && stride % 4 == 0); };
+    const int vec = (k1 % 4 == 0 && k2 % 4 == 0 && al16(in1, in1_stride) && al16(in2, in2_stride) && al16(pre_ref, pre_stride)) ? 1 : 0;
+    ColGemmArgs a{in1, in1_stride, k1, in2, in2_stride, k2, pre_ref, pre_stride, slope, part, n_rows, vec};
     cudaStream_t st = (cudaStream_t)stream;
     int rc;
     switch (round_n(k1)) {

@@ -47,11 +47,9 @@ namespace {
 constexpr int kMinSeg = 128;       // rows up to this many entries are never split
 constexpr int kThreads = 256;
 constexpr int kPartialStride = SSL_MAX_VIEWS * SSL_MAX_DIM;
-// thread-mapping / scheduling variants of prop_kernel, switchable for A/B profiling: ssl_set_option("prop_view_major" |
-// "prop_lite" | "prop_persistent", 0 / 1).  Defaults = the fastest measured on B200 (profiles/r02_prop_variants.md).
+// ssl_set_option("prop_view_major", 1): one view per thread, grid.y = view -- DRAM traffic at 1.03x compulsory instead of 1.3x,
+// but 25-40 % slower on B200 (the kernel is issue / latency bound, not DRAM bound: profiles/r02_prop_variants.md).  Default off.
 bool g_view_major = false;
-bool g_lite = false;
-bool g_persistent = false;
 
 struct PlanDev {
     const int32_t *colidx;
@@ -72,14 +70,12 @@ __device__ __forceinline__ float sgnf(float x) { return (x > 0.f) ? 1.f : ((x < 
 //         epilogue (SimGCL layer 1);  MODE 1: per-view inputs, no edge masks -> V accumulators, ONE weight per entry;
 // MODE 2: per-view edge masks -> V accumulators, V weights per entry.
 // VM (view-major): V is 1 here, the thread serves view blockIdx.y of a.n_views; MODE 1 / 2 only.
-// LITE: two entries in flight per group instead of four and 6 resident CTAs per SM instead of 4 (more independent
-// item chains per SM at the same number of outstanding row loads).
-template <int G, int V, int MODE, bool VM, bool LITE>
+template <int G, int V, int MODE, bool VM>
 __device__ __forceinline__ void prop_item(const PlanDev &p, const ssl_prop_args &a, const int64_t item_idx, const int4 it) {
     constexpr bool SHARED = MODE == 0;
     constexpr int NA = SHARED ? 1 : V;
     constexpr int NW = (MODE == 2) ? V : 1;        // distinct weights per entry
-    constexpr int UNR = LITE ? ((NA == 1 && G >= 8) ? 4 : 2) : ((NA == 1 && G >= 8) ? 8 : 4);   // entries whose row gathers are in flight together
+    constexpr int UNR = (NA == 1 && G >= 8) ? 8 : 4;   // entries whose row gathers are in flight together (single view: 8)
     static_assert(!VM || (V == 1 && MODE != 0), "view-major serves one view per thread");
     const int lane = threadIdx.x & 31;
     const int gl = lane % G;
@@ -232,52 +228,26 @@ __device__ __forceinline__ void prop_item(const PlanDev &p, const ssl_prop_args 
     }
 }
 
-constexpr int min_ctas(int V, bool lite) { return lite ? ((V <= 3) ? 6 : 4) : ((V <= 3) ? 4 : 3); }
-
-// One work item per group (grid covers the list), or -- PERSISTENT -- a resident grid whose groups stride over the list with
-// the next item's header prefetched: no CTA turnover (10 k CTAs of ~9 us each at the amazon shape) between items.
-template <int G, int V, int MODE, bool VM, bool LITE, bool PERSISTENT>
-__global__ void __launch_bounds__(kThreads, min_ctas(V, LITE)) prop_kernel(PlanDev p, ssl_prop_args a) {
+// One work item per group; the grid covers the list (blockIdx.y = view when view-major).  Tried and dropped (profiles/
+// r02_prop_variants.md): a resident grid striding over the list with the next header prefetched (1.2-1.5x slower: the hardware CTA
+// scheduler balances the uneven items better than a static stride) and a 2-deep / 6-CTA variant (1.05-1.4x slower).
+template <int G, int V, int MODE, bool VM>
+__global__ void __launch_bounds__(kThreads, (V <= 3) ? 4 : 3) prop_kernel(PlanDev p, ssl_prop_args a) {
     constexpr int RPW = 32 / G;
     const int grp = (threadIdx.x & 31) / G;
     const int64_t warp = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
-    int64_t item_idx = warp * RPW + grp;
+    const int64_t item_idx = warp * RPW + grp;
     int4 it = make_int4(-1, 0, 0, -1);
     if (item_idx < p.n_items) it = p.items[item_idx];
-    if (!PERSISTENT) {
-        prop_item<G, V, MODE, VM, LITE>(p, a, item_idx, it);
-        return;
-    }
-    const int64_t stride = (int64_t)gridDim.x * (kThreads / 32) * RPW;
-    // all groups of a warp run the same number of rounds (the shuffles inside are group-masked, but a warp must stay converged
-    // at the loop level): iterate while ANY item of the warp's round exists
-    const int64_t warp_first = warp * RPW;
-    for (int64_t base = warp_first; base < p.n_items; base += stride) {
-        const int64_t next = item_idx + stride;
-        int4 it_next = make_int4(-1, 0, 0, -1);
-        if (next < p.n_items) it_next = p.items[next];
-        prop_item<G, V, MODE, VM, LITE>(p, a, item_idx, it);
-        item_idx = next;
-        it = it_next;
-    }
+    prop_item<G, V, MODE, VM>(p, a, item_idx, it);
 }
 
 template <int G, int V, int MODE, bool VM>
 int launch_variant(const PlanDev &p, const ssl_prop_args &a, int64_t n_items, cudaStream_t st) {
     constexpr int RPW = 32 / G;
     const int64_t items_per_block = (int64_t)(kThreads / 32) * RPW;
-    const int64_t need = (n_items + items_per_block - 1) / items_per_block;
-    const unsigned ny = VM ? (unsigned)a.n_views : 1u;
-    const bool lite = g_lite, pers = g_persistent;
-    const int64_t resident = (int64_t)ssl::kNumSM * min_ctas(V, lite) / ny;      // one resident wave (split over the views when view-major)
-    const dim3 grid((unsigned)(pers ? std::min<int64_t>(need, std::max<int64_t>(resident, 1)) : need), ny);
-    if (lite) {
-        if (pers) prop_kernel<G, V, MODE, VM, true, true><<<grid, kThreads, 0, st>>>(p, a);
-        else prop_kernel<G, V, MODE, VM, true, false><<<grid, kThreads, 0, st>>>(p, a);
-    } else {
-        if (pers) prop_kernel<G, V, MODE, VM, false, true><<<grid, kThreads, 0, st>>>(p, a);
-        else prop_kernel<G, V, MODE, VM, false, false><<<grid, kThreads, 0, st>>>(p, a);
-    }
+    const dim3 grid((unsigned)((n_items + items_per_block - 1) / items_per_block), VM ? (unsigned)a.n_views : 1u);
+    prop_kernel<G, V, MODE, VM><<<grid, kThreads, 0, st>>>(p, a);
     SSL_LAUNCH_CHECK("prop_kernel");
     return SSL_OK;
 }
@@ -411,8 +381,8 @@ extern "C" int ssl_plan_create_ranges(ssl_plan **out, const int32_t *h_rowptr, c
 extern "C" int ssl_set_option(const char *name, int64_t value) {
     SSL_CHECK_ARG(name != nullptr, "ssl_set_option: null name");
     const std::string n(name);
-    if (n == "prop_view_major" || n == "prop_lite" || n == "prop_persistent") {
-        (n == "prop_view_major" ? g_view_major : (n == "prop_lite" ? g_lite : g_persistent)) = value != 0;
+    if (n == "prop_view_major") {
+        g_view_major = value != 0;
         return SSL_OK;
     }
     if (n == "prop_interleaved") {          // round-2a name: 1 = not view-major

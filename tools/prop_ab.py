@@ -54,15 +54,12 @@ def main():
         shapes = {'xl-8th fwd (d=128, 1 view, 75 M entries)': (xp, xa)}
         x, d, V, plan = xx, 128, 1, xplan
     nnz = plan.nnz
-    combos = [('interleaved', 0, 0, 0), ('view-major', 1, 0, 0), ('interleaved+persistent', 0, 0, 1), ('interleaved+lite', 0, 1, 0),
-              ('interleaved+lite+persistent', 0, 1, 1), ('view-major+lite+persistent', 1, 1, 1)]
-    if ncu:
-        combos = [c for c in combos if c[0] in ('interleaved', 'interleaved+persistent', 'interleaved+lite+persistent')]
+    combos = [('interleaved', 0), ('view-major', 1)]
+    if ncu and '--xl' in sys.argv:
+        combos = combos[:1]
     for what, (prop, args) in shapes.items():
-        for mode, vm, lite, pers in combos:
+        for mode, vm in combos:
             check(lib.ssl_set_option(b'prop_view_major', vm))
-            check(lib.ssl_set_option(b'prop_lite', lite))
-            check(lib.ssl_set_option(b'prop_persistent', pers))
             if ncu:
                 for _ in range(3):
                     prop._launch(args, x)
@@ -78,8 +75,7 @@ def main():
             ms = e0.elapsed_time(e1) / reps
             gather = nnz * (8 + 4 * d * V)
             print(json.dumps({'shape': what, 'mode': mode, 'ms': round(ms, 4), 'gather_TBps': round(gather / ms / 1e9, 2)}), flush=True)
-    for o in (b'prop_view_major', b'prop_lite', b'prop_persistent'):
-        check(lib.ssl_set_option(o, 0))
+    check(lib.ssl_set_option(b'prop_view_major', 0))
 
 
 main()
