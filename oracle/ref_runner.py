@@ -71,6 +71,9 @@ class ReferenceTrainer:
         opt = self.trainer.optimizer
         opt.zero_grad()
         batch_data = [x.long().to(self.configs['device']) for x in batch]
+        if self.configs['model']['name'] == 'ncl' and len(batch_data) == 3:      # pairwise_with_epoch_flag datasets add the flag column
+            batch_data.append(batch_data[0].new_zeros(batch_data[0].shape[0]) + (1 if not getattr(self, '_clustered', False) else 0))
+            self._clustered = True
         loss, loss_dict = self.model.cal_loss(batch_data)
         v = loss.item()
         loss.backward()
