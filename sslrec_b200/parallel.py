@@ -14,9 +14,8 @@ Exchange steps -- the only inter-GPU traffic on the path:
     every peer's allocation over NVLink), the kernel's epilogue stores each finished row to the same
     row of all peers' tables (``ssl_prop_args.x_out_peers``), so the NVLink traffic overlaps the
     gathers of the rows still being computed; what remains is a cross-GPU barrier on the stream after the
-    launch.  When the allocation has an NVSwitch multicast address (NVLS) the row is stored ONCE, to that address,
-    and the switch replicates it into all copies (the sender's egress drops from (W-1) x to 1 x the block; the bound
-    becomes each GPU's ingress).  The ``nccl`` transport (fallback, and the gloo CPU tests) all-gathers the owned row
+    launch.  (Optionally the row is stored once to the allocation's NVSwitch multicast address instead: measured equal,
+    the exchange is ingress-bound.)  The ``nccl`` transport (fallback, and the gloo CPU tests) all-gathers the owned row
     blocks with ``all_gather_into_tensor`` after the launch;
   * the updated parameters: Adam runs on the owned rows only and stores the new values to every peer's
     replica of the table (``ssl_adam_step_peers``) -- the sixth all-gather of a step, fused the same way;
@@ -111,12 +110,14 @@ class RowShard:
         if transport not in ('symm', 'nccl'):
             raise ValueError("transport must be 'symm' (fused NVLink stores) or 'nccl' (all_gather after the launch)")
         self.transport = transport
-        # symm transport: store finished rows through the NVSwitch multicast address when the allocation has one (one store per
-        # row instead of one per peer: the sender's NVLink egress drops by world - 1, the switch replicates); False = plain
-        # per-peer stores.  SSLREC_B200_MULTICAST=0/1 overrides 'auto'.
+        # symm transport, optional: store finished rows ONCE, to the NVSwitch multicast address of the table (the switch
+        # replicates; the sender's egress drops by world - 1) instead of once per peer.  Measured on 8 x B200 at BASELINE
+        # config 4 (profiles/r02_multi_gpu.md): no faster (57.9 vs 57.7 ms of SpMM per step) -- the exchange is bound by what every
+        # GPU RECEIVES (5.4 GB per layer), not by what it sends -- so the plain peer stores stay the default.
+        # multicast=True or SSLREC_B200_MULTICAST=1 selects it.
         import os
         env = os.environ.get('SSLREC_B200_MULTICAST')
-        self.multicast = (env != '0') if (multicast == 'auto' and env is not None) else (True if multicast == 'auto' else bool(multicast))
+        self.multicast = (env == '1') if multicast == 'auto' else bool(multicast)
         self._tables: Dict[tuple, SharedTable] = {}
         self._barrier_handle = None
         self.stats = dict(barriers=0, gathers=0, gathered_bytes=0)
