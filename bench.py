@@ -525,6 +525,44 @@ def run_ours(args):
                 epoch[key + '_steps_per_sec'] = len(loader) / best
                 epoch[key + '_epoch_s'] = best
 
+        # ---- the same step captured in ONE CUDA graph (sslrec_b200.graphed.GraphedStep; `train.cuda_graph: true` in the trainer) ----
+        graphed = None
+        if world == 1 and not args.no_cuda_graph and model_name in ('lightgcn', 'simgcl', 'sgl', 'directau', 'lightgcl'):
+            try:
+                from sslrec_b200.graphed import GraphedStep
+                gs = GraphedStep(model, opt, as_batch(dev_batches[0]), warmup=3)
+                gl, gp = None, None
+                for i in range(W):
+                    gs(as_batch(dev_batches[i % len(dev_batches)]))
+                res = {}
+                for key, from_host in (('resident', False), ('e2e', True)):
+                    per = []
+                    for _ in range(3):
+                        torch.cuda.synchronize()
+                        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        t_host = time.perf_counter()
+                        e0.record()
+                        for i in range(K):
+                            b = host_batches[(W + i) % len(host_batches)].to(dev, non_blocking=True) if from_host else dev_batches[(W + i) % len(dev_batches)]
+                            gl, gp = gs(as_batch(b))
+                            if from_host:
+                                reader.push(gl, gp)
+                        if from_host:
+                            reader.flush()
+                        e1.record()
+                        t_host = time.perf_counter() - t_host
+                        torch.cuda.synchronize()
+                        per.append((e0.elapsed_time(e1) / K, 1e3 * t_host / K))
+                    per.sort()
+                    res[key] = {'ms_per_step': per[1][0], 'steps_per_sec': 1e3 / per[1][0], 'host_ms_per_step': per[1][1], 'passes_ms': [p[0] for p in per]}
+                gs.close()
+                graphed = {'how': 'zero_grad + cal_loss + backward + FusedAdam.step captured once (3 eager warm-up steps), replayed per batch; seeds of the in-kernel '
+                                  'augmentation and the Adam step count are device-resident, so training is identical to the eager loop '
+                                  '(tests/test_gpu_models.py::test_cuda_graph_step_equals_eager_step); median of 3 passes of K steps',
+                           'seeds_per_step': gs.n_seeds, **res}
+            except Exception as e:      # noqa: BLE001 -- an extra record must never cost the bench line
+                graphed = {'error': repr(e)[:400]}
+
         peaks, peak_kind = measured_peaks()
         N, nnz, d = n_user + n_item, 2 * len(rows), hp['embedding_size']
         L = hp['layer_num']
@@ -632,7 +670,7 @@ def run_ours(args):
             'e2e_epoch': epoch,
             'gpu_launches': launches, 'gpu_launches_per_step': launches / K,
             'embeddings_propagated_per_sec': emb_per_step * value,
-            'roofline': roofline, 'roofline_infonce': roofline_nce, 'cpu_baseline': cpu, 'row_shard': None,
+            'roofline': roofline, 'roofline_infonce': roofline_nce, 'cpu_baseline': cpu, 'row_shard': None, 'cuda_graph': graphed,
             'roofline_note': 'roofline = the SpMM BASELINE.json names (HBM-bound); roofline_infonce = the kernel with the largest share of this '
                              'step (tensor-bound contraction); both carry share_of_step',
             'clocks': clocks, 'clocks_e2e': clocks_e2e, 'kernel_ms_per_step': {k: v['ms'] / K for k, v in summ.items()}, 'profiled_ms_per_step': prof_ms,
@@ -741,6 +779,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='simgcl-amazon', choices=sorted(WORKLOADS))
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-cuda-graph', action='store_true', help='skip the cuda_graph record (e.g. under a profiler)')
     ap.add_argument('--cpu-budget', type=float, default=170.0, help='--impl reference: wall-clock budget of the timed CPU steps (s)')
     ap.add_argument('--cpu-csr', action='store_true', help='--impl reference: adjacency converted with to_sparse_csr() ("tuned CPU")')
     ap.add_argument('--row-shard', default='auto', choices=['auto', 'on', 'off'],

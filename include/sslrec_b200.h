@@ -152,6 +152,9 @@ typedef struct ssl_prop_args {
                                          regulariser term: d loss / d reg_params is only known on the device) */
     const float *reg_src2;            /* optional second [n_cols, dim] row source added with coefficient 1 (with reduce_views):
                                          gradient rows that losses wrote for layer 0 (ncl.py:75) */
+    const uint64_t *seed_ptr[SSL_MAX_VIEWS];  /* optional: the view's seed is READ FROM THE DEVICE (overrides seed[v]) -- a step captured
+                                         in a CUDA graph draws fresh masks / noise at every replay because the host rewrites these
+                                         words, not the launch arguments */
 } ssl_prop_args;
 
 SSL_API int ssl_propagate_layer(const ssl_plan *plan, const ssl_prop_args *args, void *stream);
@@ -165,6 +168,10 @@ SSL_API int ssl_propagate_layer(const ssl_plan *plan, const ssl_prop_args *args,
 SSL_API int ssl_node_drop(const float *x, float *out, int64_t n, int32_t dim, int32_t n_views, int32_t backward,
                   const int32_t *mode, const float *keep, const uint8_t *const *mask, const uint64_t *seed,
                   int64_t row_offset, void *stream);
+/* the same with per-view seeds read from the device (seed_ptr[v] may be NULL: then seed[v] is used) */
+SSL_API int ssl_node_drop_dev(const float *x, float *out, int64_t n, int32_t dim, int32_t n_views, int32_t backward,
+                      const int32_t *mode, const float *keep, const uint8_t *const *mask, const uint64_t *seed,
+                      const uint64_t *const *seed_ptr, int64_t row_offset, void *stream);
 
 /* ------------------------------------------------------------------------------------------
  * a11+a12  gathers + BPR  (lightgcn.py:48-52, loss_utils.py:7-10; hccf.py:70-74 is the same
@@ -264,6 +271,12 @@ SSL_API int ssl_adam_step(float *p, const float *g, float *m, float *v, int64_t 
  * the table, mapped over NVLink) -- the all-gather of the updated table fused into the optimizer kernel. */
 SSL_API int ssl_adam_step_peers(float *p, float *const *p_peers, int32_t n_peers, const float *g, float *m, float *v, int64_t n,
                         int64_t step, double lr, double beta1, double beta2, double eps, double weight_decay, void *stream);
+/* The step count read from the device: *step_dev (>= 1) is the 1-based step of THIS update; the bias corrections are formed on the
+ * device (double precision, as the host path) into scratch2 (2 floats) by a one-thread launch, so that a CUDA graph holding the
+ * optimizer step replays with a counter the graph itself increments. */
+SSL_API int ssl_adam_step_dev(float *p, float *const *p_peers, int32_t n_peers, const float *g, float *m, float *v, int64_t n,
+                      const int64_t *step_dev, float *scratch2, double lr, double beta1, double beta2, double eps, double weight_decay,
+                      void *stream);
 
 /* ------------------------------------------------------------------------------------------
  * a18  full_predict + _mask_predict (lightgcn.py:58-66, base_model.py:35-36) and the top-k that
@@ -321,6 +334,9 @@ SSL_API int ssl_colgemm(const float *in1, int64_t in1_stride, int32_t k1, const 
                 const float *ref, float *out, float *out_act, void *stream);
 SSL_API int ssl_hyper_dropout(const float *x, float *out, int64_t n, int32_t h, float keep, int32_t mode, const float *mask, uint64_t seed,
                       uint32_t stream_id, int32_t accumulate, void *stream);
+/* seed read from the device (CUDA-graph replay, see ssl_prop_args.seed_ptr) */
+SSL_API int ssl_hyper_dropout_dev(const float *x, float *out, int64_t n, int32_t h, float keep, int32_t mode, const float *mask,
+                          const uint64_t *seed_ptr, uint32_t stream_id, int32_t accumulate, void *stream);
 
 /* ------------------------------------------------------------------------------------------
  * a17  KMeansClustering (aug_utils.py:142-157, NCL): one Lloyd iteration = assignment

@@ -37,7 +37,7 @@ class PropArgs(C.Structure):
         ('noise_eps', C.c_float), ('seed', C.c_uint64 * MAX_VIEWS),
         ('edge_stream_id', C.c_uint32), ('noise_stream_id', C.c_uint32),
         ('n_peers', C.c_int32), ('x_out_peers', vp * MAX_PEERS), ('sum_out_peers', vp * MAX_PEERS),
-        ('reg_coef_dev', vp), ('reg_src2', vp),
+        ('reg_coef_dev', vp), ('reg_src2', vp), ('seed_ptr', vp * MAX_VIEWS),
     ]
 
 
@@ -63,6 +63,7 @@ def _load():
         'ssl_plan_stats': (C.c_int, [vp, c_i64p]),
         'ssl_propagate_layer': (C.c_int, [vp, C.POINTER(PropArgs), vp]),
         'ssl_node_drop': (C.c_int, [vp, vp, i64, i32, i32, i32, c_i32p, c_f32p, C.POINTER(vp), C.POINTER(C.c_uint64), i64, vp]),
+        'ssl_node_drop_dev': (C.c_int, [vp, vp, i64, i32, i32, i32, c_i32p, c_f32p, C.POINTER(vp), C.POINTER(C.c_uint64), C.POINTER(vp), i64, vp]),
         'ssl_bpr_fwd': (C.c_int, [vp, i64, vp, i64, vp, vp, vp, i64, i32, vp, vp, vp]),
         'ssl_bpr_bwd': (C.c_int, [vp, i64, vp, i64, vp, vp, vp, i64, i32, vp, vp, f32, vp, i64, vp, i64, vp]),
         'ssl_rows_normalize': (C.c_int, [vp, i64, vp, i64, i32, i32, f32, vp, vp, vp, vp, vp, vp, vp, i64, vp]),
@@ -82,6 +83,8 @@ def _load():
         'ssl_colgemm_parts': (C.c_int, [i64]),
         'ssl_colgemm': (C.c_int, [vp, i64, i32, vp, i64, i32, vp, i64, f32, i64, vp, f32, i32, vp, vp, vp, vp]),
         'ssl_hyper_dropout': (C.c_int, [vp, vp, i64, i32, f32, i32, vp, C.c_uint64, C.c_uint32, i32, vp]),
+        'ssl_adam_step_dev': (C.c_int, [vp, C.POINTER(vp), i32, vp, vp, vp, i64, vp, vp, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, vp]),
+        'ssl_hyper_dropout_dev': (C.c_int, [vp, vp, i64, i32, f32, i32, vp, vp, C.c_uint32, i32, vp]),
         'ssl_predict_mask': (C.c_int, [vp, i64, vp, i64, vp, i64, i64, i32, vp, vp, vp, vp, vp]),
         'ssl_topk': (C.c_int, [vp, i64, i64, i32, vp, vp, vp]),
         'ssl_align_fwd': (C.c_int, [vp, vp, i64, i32, vp, vp]),

@@ -269,7 +269,7 @@ __global__ void colgemm_finalize_kernel(const float *__restrict__ part, int n_pa
 // dropout of the incidence, forward (out = a * keep / p) and backward (out += g * keep / p); keep test: floor(U + p) as torch's
 // Bernoulli(p) mask of F.dropout -- the in-kernel draw is keyed by (seed, stream; row, 4-column group)
 __global__ void hyper_dropout_kernel(const float *__restrict__ x, float *__restrict__ out, int64_t n, int h, float keep, int mode,
-                                     const float *__restrict__ mask, uint64_t seed, uint32_t stream, int accumulate) {
+                                     const float *__restrict__ mask, uint64_t seed, const uint64_t *__restrict__ seed_ptr, uint32_t stream, int accumulate) {
     const int quads = h / 4;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n * quads) return;
@@ -279,7 +279,8 @@ __global__ void hyper_dropout_kernel(const float *__restrict__ x, float *__restr
     float4 k;
     if (mode == 2) k = ssl::ldg4(mask + r * h + q * 4);
     else {
-        const uint4 u = ssl::philox4x32_10(make_uint4((uint32_t)r, (uint32_t)q, stream, 0x48595052u /*"HYPR"*/), ssl::seed_key(seed));
+        const uint4 u = ssl::philox4x32_10(make_uint4((uint32_t)r, (uint32_t)q, stream, 0x48595052u /*"HYPR"*/),
+                                           ssl::seed_key(seed_ptr != nullptr ? __ldg(seed_ptr) : seed));
         k = make_float4(ssl::u01(u.x) + keep >= 1.f ? 1.f : 0.f, ssl::u01(u.y) + keep >= 1.f ? 1.f : 0.f,
                         ssl::u01(u.z) + keep >= 1.f ? 1.f : 0.f, ssl::u01(u.w) + keep >= 1.f ? 1.f : 0.f);
     }
@@ -393,13 +394,24 @@ extern "C" int ssl_colgemm(const float *in1, int64_t in1_stride, int32_t k1, con
     return SSL_OK;
 }
 
-extern "C" int ssl_hyper_dropout(const float *x, float *out, int64_t n, int32_t h, float keep, int32_t mode, const float *mask, uint64_t seed,
-                                 uint32_t stream_id, int32_t accumulate, void *stream) {
+static int hyper_dropout_launch(const float *x, float *out, int64_t n, int32_t h, float keep, int32_t mode, const float *mask, uint64_t seed,
+                                const uint64_t *seed_ptr, uint32_t stream_id, int32_t accumulate, void *stream) {
     SSL_CHECK_ARG(x && out && h >= 4 && h % 4 == 0 && keep > 0.f && keep <= 1.f, "ssl_hyper_dropout: bad argument");
     SSL_CHECK_ARG(mode == 1 || (mode == 2 && mask != nullptr), "ssl_hyper_dropout: mode 1 (in-kernel draw) or 2 (injected [n, h] float keep mask)");
     const int64_t total = n * (h / 4);
     if (total == 0) return SSL_OK;
-    hyper_dropout_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, out, n, h, keep, mode, mask, seed, stream_id, accumulate);
+    hyper_dropout_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, out, n, h, keep, mode, mask, seed, seed_ptr, stream_id, accumulate);
     SSL_LAUNCH_CHECK("hyper_dropout_kernel");
     return SSL_OK;
+}
+
+extern "C" int ssl_hyper_dropout(const float *x, float *out, int64_t n, int32_t h, float keep, int32_t mode, const float *mask, uint64_t seed,
+                                 uint32_t stream_id, int32_t accumulate, void *stream) {
+    return hyper_dropout_launch(x, out, n, h, keep, mode, mask, seed, nullptr, stream_id, accumulate, stream);
+}
+
+extern "C" int ssl_hyper_dropout_dev(const float *x, float *out, int64_t n, int32_t h, float keep, int32_t mode, const float *mask,
+                                     const uint64_t *seed_ptr, uint32_t stream_id, int32_t accumulate, void *stream) {
+    SSL_CHECK_ARG(mode == 2 || seed_ptr != nullptr, "ssl_hyper_dropout_dev: seed_ptr is null");
+    return hyper_dropout_launch(x, out, n, h, keep, mode, mask, 0, seed_ptr, stream_id, accumulate, stream);
 }

@@ -343,8 +343,19 @@ struct PeerPtrs {
     float *p[SSL_MAX_PEERS];
     int n;
 };
+// bias corrections from a device-resident step count (CUDA-graph replay): double precision like the host path
+__global__ void adam_prepare_kernel(const int64_t *__restrict__ step_dev, double lr, double beta1, double beta2, float *__restrict__ out2) {
+    const double step = (double)*step_dev;
+    out2[0] = (float)(lr / (1.0 - pow(beta1, step)));
+    out2[1] = (float)(1.0 / sqrt(1.0 - pow(beta2, step)));
+}
+
 __global__ void adam_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m, float *__restrict__ v,
-                            int64_t n, AdamK k, PeerPtrs peers) {
+                            int64_t n, AdamK k, PeerPtrs peers, const float *__restrict__ dyn) {
+    if (dyn != nullptr) {
+        k.step_size = __ldg(dyn);
+        k.inv_bc2_sqrt = __ldg(dyn + 1);
+    }
     const int64_t n4 = n / 4;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
         float4 pv = *reinterpret_cast<float4 *>(p + i * 4), mv = *reinterpret_cast<float4 *>(m + i * 4),
@@ -537,9 +548,9 @@ extern "C" int ssl_axpy(const float *x, float *y, int64_t n, const float *gscale
     return SSL_OK;
 }
 
-extern "C" int ssl_adam_step_peers(float *p, float *const *p_peers, int32_t n_peers, const float *g, float *m, float *v, int64_t n,
-                                   int64_t step, double lr, double beta1, double beta2, double eps, double weight_decay, void *stream) {
-    SSL_CHECK_ARG(p && g && m && v && step >= 1, "ssl_adam_step: bad argument");
+static int adam_launch(float *p, float *const *p_peers, int32_t n_peers, const float *g, float *m, float *v, int64_t n, int64_t step,
+                       const int64_t *step_dev, float *scratch2, double lr, double beta1, double beta2, double eps, double weight_decay, void *stream) {
+    SSL_CHECK_ARG(p && g && m && v && (step >= 1 || (step_dev != nullptr && scratch2 != nullptr)), "ssl_adam_step: bad argument");
     SSL_CHECK_ARG(((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v)) & 15) == 0,
                   "ssl_adam_step: pointers must be 16-byte aligned");
     SSL_CHECK_ARG(n_peers >= 0 && n_peers <= SSL_MAX_PEERS && (n_peers == 0 || p_peers != nullptr), "ssl_adam_step_peers: bad peer list");
@@ -550,15 +561,34 @@ extern "C" int ssl_adam_step_peers(float *p, float *const *p_peers, int32_t n_pe
         peers.p[q] = p_peers[q];
     }
     if (n == 0) return SSL_OK;
-    const double bc1 = 1.0 - std::pow(beta1, (double)step);
-    const double bc2 = 1.0 - std::pow(beta2, (double)step);
-    const float step_size = (float)(lr / bc1);
-    const float inv_bc2_sqrt = (float)(1.0 / std::sqrt(bc2));
+    float step_size = 0.f, inv_bc2_sqrt = 0.f;
+    if (step_dev == nullptr) {
+        const double bc1 = 1.0 - std::pow(beta1, (double)step);
+        const double bc2 = 1.0 - std::pow(beta2, (double)step);
+        step_size = (float)(lr / bc1);
+        inv_bc2_sqrt = (float)(1.0 / std::sqrt(bc2));
+    } else {
+        adam_prepare_kernel<<<1, 1, 0, STREAM>>>(step_dev, lr, beta1, beta2, scratch2);
+        SSL_LAUNCH_CHECK("adam_prepare_kernel");
+    }
     const int blocks = (int)std::min<int64_t>(ssl::kNumSM * 8, (n / 4 + 255) / 256 + 1);
     const AdamK k{(float)beta1, (float)beta2, (float)(1.0 - beta1), (float)(1.0 - beta2), step_size, inv_bc2_sqrt, (float)eps, (float)weight_decay};
-    adam_kernel<<<blocks, 256, 0, STREAM>>>(p, g, m, v, n, k, peers);
+    adam_kernel<<<blocks, 256, 0, STREAM>>>(p, g, m, v, n, k, peers, step_dev != nullptr ? scratch2 : nullptr);
     SSL_LAUNCH_CHECK("adam_kernel");
     return SSL_OK;
+}
+
+extern "C" int ssl_adam_step_peers(float *p, float *const *p_peers, int32_t n_peers, const float *g, float *m, float *v, int64_t n,
+                                   int64_t step, double lr, double beta1, double beta2, double eps, double weight_decay, void *stream) {
+    SSL_CHECK_ARG(step >= 1, "ssl_adam_step: step must be >= 1");
+    return adam_launch(p, p_peers, n_peers, g, m, v, n, step, nullptr, nullptr, lr, beta1, beta2, eps, weight_decay, stream);
+}
+
+extern "C" int ssl_adam_step_dev(float *p, float *const *p_peers, int32_t n_peers, const float *g, float *m, float *v, int64_t n,
+                                 const int64_t *step_dev, float *scratch2, double lr, double beta1, double beta2, double eps, double weight_decay,
+                                 void *stream) {
+    SSL_CHECK_ARG(step_dev != nullptr && scratch2 != nullptr, "ssl_adam_step_dev: step_dev / scratch2 is null");
+    return adam_launch(p, p_peers, n_peers, g, m, v, n, 0, step_dev, scratch2, lr, beta1, beta2, eps, weight_decay, stream);
 }
 
 extern "C" int ssl_adam_step(float *p, const float *g, float *m, float *v, int64_t n, int64_t step, double lr, double beta1,

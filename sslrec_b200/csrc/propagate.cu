@@ -64,6 +64,9 @@ struct PlanDev {
     uint32_t off_a, off_b;
 };
 
+// the view's RNG seed: a launch argument, or -- CUDA-graph replay -- a word the host rewrites on the device
+__device__ __forceinline__ uint64_t view_seed(const ssl_prop_args &a, int v) { return a.seed_ptr[v] != nullptr ? __ldg(a.seed_ptr[v]) : a.seed[v]; }
+
 __device__ __forceinline__ float sgnf(float x) { return (x > 0.f) ? 1.f : ((x < 0.f) ? -1.f : 0.f); }
 
 // MODE 0: all views read the same input row and no view masks edges -> one accumulator, perturbed per view in the
@@ -109,7 +112,7 @@ __device__ __forceinline__ void prop_item(const PlanDev &p, const ssl_prop_args 
                 if (mode == 1) {
                     const uint32_t kr = a.transpose ? (uint32_t)c : grow;
                     const uint32_t kc = a.transpose ? grow : (uint32_t)c;
-                    f = (valid && ssl::edge_keep_rng(a.seed[vbase + v], a.edge_stream_id, kr, kc, a.edge_keep[vbase + v])) ? w * a.edge_scale[vbase + v] : 0.f;
+                    f = (valid && ssl::edge_keep_rng(view_seed(a, vbase + v), a.edge_stream_id, kr, kc, a.edge_keep[vbase + v])) ? w * a.edge_scale[vbase + v] : 0.f;
                 } else if (mode == 2) {
                     const int q = valid ? (a.transpose ? __ldg(p.rev + pe) : pe) : 0;
                     f = (valid && a.edge_mask[vbase + v][q]) ? w * a.edge_scale[vbase + v] : 0.f;
@@ -186,7 +189,7 @@ __device__ __forceinline__ void prop_item(const PlanDev &p, const ssl_prop_args 
         if (nm != 0) {
             float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
             if (lane_on) {
-                if (nm == 1) u = ssl::noise_u4_rng(a.seed[v], a.noise_stream_id, grow, (uint32_t)gl);
+                if (nm == 1) u = ssl::noise_u4_rng(view_seed(a, v), a.noise_stream_id, grow, (uint32_t)gl);
                 else u = ssl::ldg4(a.noise_u[v] + (size_t)grow * dim + col);
             }
             float ss = u.x * u.x + u.y * u.y + u.z * u.z + u.w * u.w;
@@ -456,6 +459,7 @@ struct NodeArgs {
     float keep[SSL_MAX_VIEWS];
     const uint8_t *mask[SSL_MAX_VIEWS];
     uint64_t seed[SSL_MAX_VIEWS];
+    const uint64_t *seed_ptr[SSL_MAX_VIEWS];
 };
 
 __global__ void node_drop_kernel(const float *__restrict__ x, float *__restrict__ out, int64_t n, int dim, int n_views,
@@ -470,7 +474,7 @@ __global__ void node_drop_kernel(const float *__restrict__ x, float *__restrict_
     if (!backward) xin = ssl::ldg4(x + r * dim + q * 4);
     for (int v = 0; v < n_views; ++v) {
         bool keep = true;
-        if (na.mode[v] == 1) keep = ssl::node_keep_rng(na.seed[v], row_offset + (uint32_t)r, na.keep[v]);
+        if (na.mode[v] == 1) keep = ssl::node_keep_rng(na.seed_ptr[v] != nullptr ? __ldg(na.seed_ptr[v]) : na.seed[v], row_offset + (uint32_t)r, na.keep[v]);
         else if (na.mode[v] == 2) keep = na.mask[v][r] != 0;
         if (!backward) {
             *reinterpret_cast<float4 *>(out + ((size_t)r * n_views + v) * dim + q * 4) = keep ? xin : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -490,11 +494,18 @@ __global__ void node_drop_kernel(const float *__restrict__ x, float *__restrict_
 extern "C" int ssl_node_drop(const float *x, float *out, int64_t n, int32_t dim, int32_t n_views, int32_t backward,
                              const int32_t *mode, const float *keep, const uint8_t *const *mask, const uint64_t *seed,
                              int64_t row_offset, void *stream) {
+    return ssl_node_drop_dev(x, out, n, dim, n_views, backward, mode, keep, mask, seed, nullptr, row_offset, stream);
+}
+
+extern "C" int ssl_node_drop_dev(const float *x, float *out, int64_t n, int32_t dim, int32_t n_views, int32_t backward,
+                                 const int32_t *mode, const float *keep, const uint8_t *const *mask, const uint64_t *seed,
+                                 const uint64_t *const *seed_ptr, int64_t row_offset, void *stream) {
     SSL_CHECK_ARG(x && out && mode && keep && seed, "ssl_node_drop: null argument");
     SSL_CHECK_ARG(dim >= 4 && dim % 4 == 0 && n_views >= 1 && n_views <= SSL_MAX_VIEWS, "ssl_node_drop: bad shape");
     NodeArgs na{};
     for (int v = 0; v < n_views; ++v) {
         na.mode[v] = mode[v]; na.keep[v] = keep[v]; na.seed[v] = seed[v];
+        na.seed_ptr[v] = seed_ptr ? seed_ptr[v] : nullptr;
         na.mask[v] = mask ? mask[v] : nullptr;
         SSL_CHECK_ARG(mode[v] != 2 || na.mask[v], "ssl_node_drop: injected mask missing for view %d", v);
     }

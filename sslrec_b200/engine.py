@@ -134,15 +134,69 @@ def splitmix64(x: int) -> int:
     return z ^ (z >> 31)
 
 
+class DevSeed(int):
+    """A kernel seed whose current value also lives in a device word (``ptr``): launches pass the pointer, so a step captured
+    in a CUDA graph reads whatever the host wrote there before the replay."""
+    ptr: int = 0
+
+
 class SeedStream:
-    """Per-model stream of 64-bit kernel seeds derived from the training seed (``train.seed``)."""
+    """Per-model stream of 64-bit kernel seeds derived from the training seed (``train.seed``).
+
+    Device mode (CUDA-graph capture, ``graphed.GraphedStep``): ``begin_step`` draws the next ``n`` seeds of the SAME sequence,
+    copies them into a device buffer, and ``next()`` hands them out in order as :class:`DevSeed` (value + address) -- the eager
+    and the graphed step therefore draw identical masks / noise."""
 
     def __init__(self, seed: int):
         self.state = splitmix64(int(seed) & 0xFFFFFFFFFFFFFFFF)
+        self.count = 0                   # seeds handed out so far (graphed.GraphedStep counts a step's draws with it)
+        self._dev = None                 # (device int64 buffer, pinned host staging buffer)
+        self._step_vals: List[int] = []
+        self._cursor = 0
 
-    def next(self) -> int:
+    def _advance(self) -> int:
         self.state = splitmix64(self.state)
         return self.state
+
+    def next(self) -> int:
+        self.count += 1
+        if self._dev is None:
+            return self._advance()
+        if self._cursor >= len(self._step_vals):
+            raise RuntimeError('more seeds drawn in this step than begin_step() provided (the step is not the captured one)')
+        v = DevSeed(self._step_vals[self._cursor])
+        v.ptr = self._dev[0].data_ptr() + 8 * self._cursor
+        self._cursor += 1
+        return v
+
+    def enable_device(self, device, capacity: int = 64, ring: int = 16) -> None:
+        # a ring of pinned staging rows: the host runs ahead of the GPU, so a row is rewritten only after its copy has executed
+        self._dev = (torch.zeros(capacity, dtype=torch.int64, device=device), torch.zeros(ring, capacity, dtype=torch.int64).pin_memory())
+        self._ring_events = [None] * ring
+        self._ring_pos = 0
+
+    def disable_device(self) -> None:
+        self._dev, self._step_vals, self._cursor = None, [], 0
+
+    def begin_step(self, n: int) -> None:
+        """Draw this step's ``n`` seeds and enqueue their host -> device copy on the current stream."""
+        dev, ring = self._dev
+        if n > dev.numel():
+            raise RuntimeError('seed buffer too small')
+        self._step_vals = [self._advance() for _ in range(n)]
+        self._cursor = 0
+        if n == 0:
+            return
+        k = self._ring_pos
+        self._ring_pos = (k + 1) % ring.shape[0]
+        if self._ring_events[k] is not None:
+            self._ring_events[k].synchronize()
+        host = ring[k]
+        host[:n] = torch.tensor([v - (1 << 64) if v >= (1 << 63) else v for v in self._step_vals], dtype=torch.int64)     # same 64 bits, signed
+        dev[:n].copy_(host[:n], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(dev.device))
+        self._ring_events[k] = ev
 
 
 # ------------------------------------------------------------------------------------------------
@@ -277,7 +331,8 @@ class Propagation:
             a.edge_mode[i] = v.edge_mode
             a.edge_keep[i] = v.keep
             a.edge_scale[i] = v.scale
-            a.seed[i] = v.seed
+            a.seed[i] = int(v.seed)
+            a.seed_ptr[i] = getattr(v.seed, 'ptr', 0) or None
             m = v.edge_mask_for(layer)
             a.edge_mask[i] = _ptr(m)
             if not transpose:
@@ -303,13 +358,14 @@ class Propagation:
         mode = (C.c_int32 * V)(*[v.node_mode for v in self.views])
         keep = (C.c_float * V)(*[v.node_keep for v in self.views])
         masks = (C.c_void_p * V)(*[_ptr(v.node_mask) for v in self.views])
-        seeds = (C.c_uint64 * V)(*[v.seed for v in self.views])
+        seeds = (C.c_uint64 * V)(*[int(v.seed) for v in self.views])
+        seed_ptrs = (C.c_void_p * V)(*[(getattr(v.seed, 'ptr', 0) or None) for v in self.views])
         n = out.shape[0] if backward else x.shape[0]
         with torch.cuda.device(x.device):
             # the table is full height on every rank (a row-sharded plan shards the SpMM, not NodeDrop): the RNG is keyed by
             # the global row, so the offset of row 0 is 0 whatever the plan owns
-            check(lib.ssl_node_drop(x.data_ptr(), out.data_ptr(), n, x.shape[-1], V, int(backward), mode, keep, masks, seeds,
-                                    0, _stream(x)), 'ssl_node_drop')
+            check(lib.ssl_node_drop_dev(x.data_ptr(), out.data_ptr(), n, x.shape[-1], V, int(backward), mode, keep, masks, seeds, seed_ptrs,
+                                        0, _stream(x)), 'ssl_node_drop')
 
     # ---- output tables ---------------------------------------------------------------------------
     def _out(self, key, shape, ref: torch.Tensor):
@@ -1151,8 +1207,13 @@ def _drop(x: torch.Tensor, d: HyperDrop, out: Optional[torch.Tensor] = None, acc
     out = torch.empty_like(x) if out is None else out
     mask = None if d.mask is None else d.mask.to(torch.float32).contiguous()
     with torch.cuda.device(x.device):
-        check(lib.ssl_hyper_dropout(x.data_ptr(), out.data_ptr(), x.shape[0], x.shape[1], d.keep, 2 if mask is not None else 1, _ptr(mask),
-                                    d.seed, d.stream, int(accumulate), _stream(x)), 'ssl_hyper_dropout')
+        ptr = getattr(d.seed, 'ptr', 0)
+        if ptr and mask is None:
+            check(lib.ssl_hyper_dropout_dev(x.data_ptr(), out.data_ptr(), x.shape[0], x.shape[1], d.keep, 1, None, ptr, d.stream, int(accumulate),
+                                            _stream(x)), 'ssl_hyper_dropout_dev')
+        else:
+            check(lib.ssl_hyper_dropout(x.data_ptr(), out.data_ptr(), x.shape[0], x.shape[1], d.keep, 2 if mask is not None else 1, _ptr(mask),
+                                        int(d.seed), d.stream, int(accumulate), _stream(x)), 'ssl_hyper_dropout')
     return out
 
 

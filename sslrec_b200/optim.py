@@ -18,6 +18,24 @@ class FusedAdam(torch.optim.Optimizer):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
         self.row_shards = dict(row_shards or {})          # keyed by id(param)
         self.comm = comm
+        self._step_dev = None         # CUDA-graph mode: the step count lives on the device (enable_device_step)
+
+    def enable_device_step(self, device) -> None:
+        """Keep the 1-based step count in a device word that the optimizer step itself increments, and form the bias corrections on
+        the device (``ssl_adam_step_dev``): a captured step then replays correctly.  The count continues from the host's."""
+        steps = {int(st['step']) for st in self.state.values() if st}
+        if len(steps) > 1:
+            raise RuntimeError('parameters with different step counts cannot share the device counter')
+        self._step_dev = torch.full((1,), steps.pop() if steps else 0, dtype=torch.int64, device=device)
+        self._dyn = {}
+
+    def disable_device_step(self) -> None:
+        if self._step_dev is not None:
+            n = int(self._step_dev.item())
+            for st in self.state.values():
+                if st:
+                    st['step'] = n
+        self._step_dev = None
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -38,9 +56,12 @@ class FusedAdam(torch.optim.Optimizer):
                     st['step'] = 0
                     st['exp_avg'] = torch.zeros_like(p, memory_format=torch.contiguous_format)
                     st['exp_avg_sq'] = torch.zeros_like(p, memory_format=torch.contiguous_format)
-                st['step'] += 1
+                if self._step_dev is None:
+                    st['step'] += 1
                 g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
                 todo.append((p, g, st))
+            if self._step_dev is not None and todo:
+                self._step_dev.add_(1)
             sharded = [p for p, _, _ in todo if id(p) in self.row_shards]
             if sharded and self.comm is not None:
                 self.comm.barrier()          # every rank has finished reading the old parameters (backward) before any peer store
@@ -52,7 +73,14 @@ class FusedAdam(torch.optim.Optimizer):
                     raise RuntimeError('FusedAdam: parameters must be contiguous')
                 with torch.cuda.device(p.device):
                     stream = torch.cuda.current_stream(p.device).cuda_stream
-                    if id(p) in self.row_shards:
+                    if self._step_dev is not None:
+                        if id(p) in self.row_shards:
+                            raise RuntimeError('the device step counter is for single-GPU CUDA-graph replay; row-sharded parameters use the host counter')
+                        dyn = self._dyn.setdefault(id(p), torch.empty(2, dtype=torch.float32, device=p.device))
+                        check(lib.ssl_adam_step_dev(p.data_ptr(), None, 0, g.data_ptr(), st['exp_avg'].data_ptr(), st['exp_avg_sq'].data_ptr(), p.numel(),
+                                                    self._step_dev.data_ptr(), dyn.data_ptr(), group['lr'], b1, b2, group['eps'], group['weight_decay'],
+                                                    stream), 'ssl_adam_step_dev')
+                    elif id(p) in self.row_shards:
                         lo, hi, peers = self.row_shards[id(p)][:3]
                         w = p.shape[1] if p.dim() > 1 else 1
                         off = 4 * lo * w

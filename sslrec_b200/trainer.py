@@ -32,6 +32,7 @@ class Trainer(object):
         self.data_handler = data_handler
         self.logger = logger
         self.grad_sync = grad_sync     # parallel.BatchShard: data-parallel ranks average gradients before the step
+        self._graphed = None           # graphed.GraphedStep when train.cuda_graph is set
 
     def create_optimizer(self, model):
         optim_config = configs['optimizer']
@@ -53,14 +54,20 @@ class Trainer(object):
         ep_loss = 0
         model.train()
         reader = LossReader(configs['device'])
+        use_graph = bool(configs['train'].get('cuda_graph', False))       # optional key: replay the step as ONE CUDA graph launch
+        if use_graph and self.grad_sync is not None:
+            raise RuntimeError('train.cuda_graph captures a single-GPU step (no gradient exchange inside)')
         for _, tem in enumerate(train_dataloader):
-            self.optimizer.zero_grad()
             batch_data = list(map(lambda x: x.long().to(configs['device'], non_blocking=True), tem))
-            loss, loss_dict = model.cal_loss(batch_data)
-            loss.backward()
-            if self.grad_sync is not None:
-                self.grad_sync.average_gradients(model.parameters())
-            self.optimizer.step()
+            if use_graph:
+                loss, loss_dict = self._graph_step(model, batch_data)
+            else:
+                self.optimizer.zero_grad()
+                loss, loss_dict = model.cal_loss(batch_data)
+                loss.backward()
+                if self.grad_sync is not None:
+                    self.grad_sync.average_gradients(model.parameters())
+                self.optimizer.step()
             for done in reader.push(loss, loss_dict):
                 ep_loss += done[0]
                 for loss_name, val in done[1].items():
@@ -72,6 +79,22 @@ class Trainer(object):
         if self.logger is not None:
             self.logger.log_loss(epoch_idx, loss_log_dict, save_to_log=configs['train'].get('log_loss', True))
         return ep_loss, loss_log_dict
+
+    def _graph_step(self, model, batch_data):
+        """The step through graphed.GraphedStep: the first full-size batch is stepped eagerly (that is the capture's warm-up -- every
+        batch is trained on exactly once, like the eager loop) and captured; later full-size batches replay the graph; a batch of
+        another size (the epoch's last) runs eagerly with the same device-resident seeds."""
+        from .graphed import GraphedStep
+        g = self._graphed
+        if g is not None and g.model is not model:
+            g.close()
+            g = self._graphed = None
+        if g is None:
+            g = self._graphed = GraphedStep(model, self.optimizer, batch_data, warmup=1)
+            return g.warm_result
+        if all(a.shape == b.shape for a, b in zip(batch_data, g.static_batch)):
+            return g(batch_data)
+        return g.eager(batch_data)
 
     def train(self, model):
         """trainer.py:86-137: plain run (evaluate every ``test_step`` epochs, then test + save) or, when the YAML

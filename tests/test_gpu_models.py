@@ -171,3 +171,74 @@ def test_trainer_epochs_and_evaluate(name):
     dense = torch.from_numpy((trn.tocsr()[:64].toarray() != 0).astype(np.int64)).cuda()
     with torch.no_grad():
         assert torch.equal(model.full_predict([users, dense]), model.full_predict([users, 'train']))
+
+
+@pytest.mark.parametrize('name', ['lightgcn', 'simgcl', 'sgl', 'sgl_nd'])
+def test_cuda_graph_step_equals_eager_step(name):
+    """graphed.GraphedStep: the captured step replayed on new batches with device-resident seeds / step count trains exactly like
+    the eager loop -- same in-kernel masks and noise (the SeedStream sequence is shared), same losses, same parameters."""
+    from sslrec_b200.graphed import GraphedStep
+    from sslrec_b200.optim import FusedAdam
+    size = 'tiny' if name == 'sgl_nd' else 'small'
+    g = replay.load_golden(name, size)
+    case = inputs.make_case(size)
+    rs = np.random.RandomState(3)
+    B = case['batch']
+    batches = []
+    for _ in range(5):
+        pick = rs.randint(0, len(case['rows']), size=B)
+        batches.append([torch.from_numpy(np.asarray(a)).long().cuda() for a in (case['rows'][pick], case['cols'][pick], rs.randint(0, case['n_item'], size=B))])
+    out = {}
+    for mode in ('eager', 'graph'):
+        model, _ = H.make_model(name, case, g['hp'])
+        model.load_state_dict({'user_embeds': case['user_e'], 'item_embeds': case['item_e']})
+        opt = FusedAdam(model.parameters(), lr=1e-2)
+        losses = []
+        if mode == 'eager':
+            for b in [batches[0]] * 2 + batches[1:]:
+                opt.zero_grad()
+                loss, parts = model.cal_loss(b)
+                loss.backward()
+                opt.step()
+                losses.append(loss.item())
+        else:
+            step = GraphedStep(model, opt, batches[0], warmup=2)          # two eager steps on batch 0, then the capture
+            losses += [float('nan')] * 2
+            assert step.n_seeds == {'lightgcn': 1, 'simgcl': 2, 'sgl': 2, 'sgl_nd': 2}[name]
+            for b in batches[1:]:
+                loss, parts = step(b)
+                losses.append(loss.item())
+            step.close()
+            assert all(int(st['step']) == 6 for st in opt.state.values())          # the device counter came back to the host
+            # and the eager path continues from the same seed sequence afterwards
+        out[mode] = (losses, torch.cat([model.user_embeds.detach(), model.item_embeds.detach()]).clone())
+    for a, b in zip(out['graph'][0][2:], out['eager'][0][2:]):
+        assert abs(a - b) <= 1e-6 * max(1.0, abs(b)), (name, out['graph'][0], out['eager'][0])
+    assert torch.allclose(out['graph'][1], out['eager'][1], rtol=1e-5, atol=3e-4), (name, (out['graph'][1] - out['eager'][1]).abs().max().item())
+
+
+def test_trainer_cuda_graph_epoch_matches_eager_epoch():
+    """Trainer.train_epoch with train.cuda_graph: the same per-epoch loss as the eager loop on the same loader order (device loader,
+    fixed seed), including the epoch's last, smaller batch."""
+    import types
+    from sslrec_b200.config import configs
+    from sslrec_b200.data_handler import DeviceLoader, DeviceTrnData
+    from sslrec_b200.trainer import Trainer
+    g = replay.load_golden('simgcl', 'small')
+    case = inputs.make_case('small')
+    res = {}
+    for graph in (False, True):
+        model, dh = H.make_model('simgcl', case, g['hp'])
+        model.load_state_dict({'user_embeds': case['user_e'], 'item_embeds': case['item_e']})
+        configs['train']['cuda_graph'] = graph
+        configs['train']['batch_size'] = 512
+        loader = DeviceLoader(DeviceTrnData(dh.trn_mat, 'cuda', 2023), 512, seed=2023)
+        tr = Trainer(types.SimpleNamespace(train_dataloader=loader))
+        tr.create_optimizer(model)
+        ep = [tr.train_epoch(model, e)[0] for e in range(2)]
+        res[graph] = (ep, model.user_embeds.detach().clone())
+        assert len(loader) >= 3 and len(loader.dataset) % 512 != 0          # the last batch is smaller: eager path inside the graphed epoch
+    configs['train']['cuda_graph'] = False
+    for a, b in zip(res[True][0], res[False][0]):
+        assert abs(a - b) <= 1e-5 * max(1.0, abs(b)), res
+    assert torch.allclose(res[True][1], res[False][1], rtol=1e-5, atol=3e-4)

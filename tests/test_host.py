@@ -29,13 +29,13 @@ def test_prop_args_struct_matches_header_layout():
     """ctypes mirror vs the C struct: compile a tiny C program against the header and compare sizeof/offsetof."""
     import ctypes, subprocess, tempfile
     from sslrec_b200 import _lib
-    src = '#include <stdio.h>\n#include <stddef.h>\n#include "sslrec_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(ssl_prop_args), offsetof(ssl_prop_args, sum_src), offsetof(ssl_prop_args, edge_mask), offsetof(ssl_prop_args, seed), offsetof(ssl_prop_args, noise_stream_id), offsetof(ssl_prop_args, sum_out_peers), offsetof(ssl_prop_args, reg_src2));return 0;}'
+    src = '#include <stdio.h>\n#include <stddef.h>\n#include "sslrec_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(ssl_prop_args), offsetof(ssl_prop_args, sum_src), offsetof(ssl_prop_args, edge_mask), offsetof(ssl_prop_args, seed), offsetof(ssl_prop_args, noise_stream_id), offsetof(ssl_prop_args, sum_out_peers), offsetof(ssl_prop_args, reg_src2), offsetof(ssl_prop_args, seed_ptr));return 0;}'
     with tempfile.TemporaryDirectory() as d:
         open(os.path.join(d, 't.c'), 'w').write(src)
         subprocess.run(['gcc', '-I', os.path.join(ROOT, 'include'), os.path.join(d, 't.c'), '-o', os.path.join(d, 't')], check=True)
         out = subprocess.run([os.path.join(d, 't')], capture_output=True, text=True, check=True).stdout.split()
     P = _lib.PropArgs
-    assert [int(x) for x in out] == [ctypes.sizeof(P), P.sum_src.offset, P.edge_mask.offset, P.seed.offset, P.noise_stream_id.offset, P.sum_out_peers.offset, P.reg_src2.offset]
+    assert [int(x) for x in out] == [ctypes.sizeof(P), P.sum_src.offset, P.edge_mask.offset, P.seed.offset, P.noise_stream_id.offset, P.sum_out_peers.offset, P.reg_src2.offset, P.seed_ptr.offset]
 
 
 def test_normalized_adjacency_matches_oracle_bits():
