@@ -48,14 +48,23 @@ __global__ void __launch_bounds__(kT) rowgemm_kernel(RowGemmArgs a) {
     float *s_m = sm;                              // [K][ldm]
     float *s_in = sm + (size_t)K * ldm;           // [TR][K + 1]
     const int ldi = K + 1;
-    for (int i = threadIdx.x; i < K * ldm; i += kT) {
-        const int k = i / ldm, c = i % ldm;
-        float v = 0.f;
-        if (c < NO) {
-            if (k < a.k1) v = a.m1_trans ? __ldg(a.m1 + (size_t)c * a.k1 + k) : __ldg(a.m1 + (size_t)k * NO + c);
-            else v = a.m2_trans ? __ldg(a.m2 + (size_t)c * a.k2 + (k - a.k1)) : __ldg(a.m2 + (size_t)(k - a.k1) * NO + c);
+    // stage M1 | M2 as [K][ldm] (zero padded): global reads run along the SOURCE's fastest dimension in either orientation
+    for (int i = threadIdx.x; i < K * (ldm - NO); i += kT) s_m[(i / (ldm - NO)) * ldm + NO + i % (ldm - NO)] = 0.f;
+    for (int part = 0; part < 2; ++part) {
+        const float *m = part ? a.m2 : a.m1;
+        const int kk = part ? a.k2 : a.k1, k0 = part ? a.k1 : 0, trans = part ? a.m2_trans : a.m1_trans;
+        if (m == nullptr || kk == 0) continue;
+        if (trans) {            // m [NO][kk]
+            for (int i = threadIdx.x; i < NO * kk; i += kT) {
+                const int c = i / kk, k = i - c * kk;
+                s_m[(size_t)(k0 + k) * ldm + c] = __ldg(m + i);
+            }
+        } else {                // m [kk][NO]
+            for (int i = threadIdx.x; i < kk * NO; i += kT) {
+                const int k = i / NO, c = i - k * NO;
+                s_m[(size_t)(k0 + k) * ldm + c] = __ldg(m + i);
+            }
         }
-        s_m[i] = v;
     }
     const int tc = threadIdx.x % 16, tr = threadIdx.x / 16;       // 16 column groups x 16 row groups (4 rows each)
     const int64_t n_tiles = (a.n_rows + TR - 1) / TR;
@@ -254,12 +263,23 @@ __global__ void __launch_bounds__(kT) colgemm_kernel(ColGemmArgs a) {
 
 // out[e] = post(sum_c part[c, e]);  post: * scale, then mode 0: identity (and out_act = leaky(out));
 //                                          mode 1: * (ref[e] > 0 ? 1 : slope)   (derivative of the activation at the saved pre-activation)
-__global__ void colgemm_finalize_kernel(const float *__restrict__ part, int n_part, int64_t n_elem, float scale, int mode, float slope,
-                                        const float *__restrict__ ref, float *__restrict__ out, float *__restrict__ out_act) {
-    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= n_elem) return;
+// block = 32 elements x 8 lanes over the partials: lane l adds partials l, l + 8, ... in order, the 8 lane sums are added in lane
+// order -- a fixed summation order for every element (bit-reproducible), 8-way parallel, 128-byte coalesced reads
+__global__ void __launch_bounds__(256) colgemm_finalize_kernel(const float *__restrict__ part, int n_part, int64_t n_elem, float scale, int mode,
+                                                               float slope, const float *__restrict__ ref, float *__restrict__ out,
+                                                               float *__restrict__ out_act) {
+    __shared__ float sh[8][33];
+    const int ex = threadIdx.x & 31, lane = threadIdx.x >> 5;
+    const int64_t e = (int64_t)blockIdx.x * 32 + ex;
     float s = 0.f;
-    for (int c = 0; c < n_part; ++c) s += part[(size_t)c * n_elem + e];
+    if (e < n_elem)
+        for (int c = lane; c < n_part; c += 8) s += part[(size_t)c * n_elem + e];
+    sh[lane][ex] = s;
+    __syncthreads();
+    if (lane != 0 || e >= n_elem) return;
+    s = sh[0][ex];
+#pragma unroll
+    for (int l = 1; l < 8; ++l) s += sh[l][ex];
     s *= scale;
     if (mode == 1) s *= (ref[e] > 0.f) ? 1.f : slope;
     out[e] = s;
@@ -310,7 +330,7 @@ int launch_rowgemm(const RowGemmArgs &a, cudaStream_t st) {
         if (dev >= 0 && dev < 64) configured[dev] = true;
     }
     const int64_t n_tiles = (a.n_rows + TR - 1) / TR;
-    const int grid = (int)std::min<int64_t>(n_tiles, 3 * ssl::kNumSM);
+    const int grid = (int)std::min<int64_t>(n_tiles, 2 * ssl::kNumSM);
     rowgemm_kernel<CPT><<<grid, kT, smem, st>>>(a);
     SSL_LAUNCH_CHECK("rowgemm_kernel");
     return SSL_OK;
@@ -366,7 +386,7 @@ extern "C" int ssl_rowgemm(const float *in1, int64_t in1_stride, int32_t k1, con
 
 extern "C" int ssl_colgemm_parts(int64_t n_rows) {
     const int64_t n_tiles = (n_rows + TR - 1) / TR;
-    return (int)std::max<int64_t>(1, std::min<int64_t>(n_tiles, 4 * ssl::kNumSM));
+    return (int)std::max<int64_t>(1, std::min<int64_t>(n_tiles, 3 * ssl::kNumSM));
 }
 
 extern "C" int ssl_colgemm(const float *in1, int64_t in1_stride, int32_t k1, const float *in2, int64_t in2_stride, int32_t k2,
@@ -389,7 +409,7 @@ extern "C" int ssl_colgemm(const float *in1, int64_t in1_stride, int32_t k1, con
     }
     if (rc != SSL_OK) return rc;
     const int64_t n_elem = (int64_t)k1 * k2;
-    colgemm_finalize_kernel<<<(unsigned)((n_elem + 255) / 256), 256, 0, st>>>(part, grid, n_elem, scale, mode, slope, ref, out, out_act);
+    colgemm_finalize_kernel<<<(unsigned)((n_elem + 31) / 32), 256, 0, st>>>(part, grid, n_elem, scale, mode, slope, ref, out, out_act);
     SSL_LAUNCH_CHECK("colgemm_finalize_kernel");
     return SSL_OK;
 }

@@ -43,19 +43,22 @@ def main():
     e_ = plain._args(d, 1, True); e_.in_views, e_.x_in, e_.sum_out, e_.reduce_views, e_.residual = V, x.data_ptr(), out2.data_ptr(), 1, res.data_ptr()
     shapes['bwd last layer (reduce over views; interleaved only)'] = (plain, e_)
     # the HBM-bound regime: one GPU's eighth of BASELINE config 4 (1.5 M nodes, 75 M entries, d = 128, one view)
-    if '--xl' in sys.argv:
-        keys = S.bipartite_keys_device(1_250_000, 250_000, 37_500_000, 2023, 1.0, 'cuda')
-        rp, ci, va = S.normalized_csr_device(keys, 1_250_000, 250_000)
-        xplan = GraphPlan.from_csr(rp, ci, va, 1_500_000, side_split=1_250_000)
-        xx = torch.randn(1_500_000, 1, 128, device='cuda') * 0.1
+    if '--xl' in sys.argv or '--xlfull' in sys.argv:
+        sc = 8 if '--xlfull' in sys.argv else 1            # --xlfull: the whole BASELINE config 4 (12 M nodes, 600 M entries, 6.1 GB table)
+        nu_x, ni_x = 1_250_000 * sc, 250_000 * sc
+        keys = S.bipartite_keys_device(nu_x, ni_x, 37_500_000 * sc, 2023, 1.0, 'cuda')
+        rp, ci, va = S.normalized_csr_device(keys, nu_x, ni_x)
+        del keys
+        xplan = GraphPlan.from_csr(rp, ci, va, nu_x + ni_x, side_split=nu_x)
+        xx = torch.randn(nu_x + ni_x, 1, 128, device='cuda') * 0.1
         xo = torch.empty_like(xx)
         xp = E.Propagation(xplan, [E.ViewSpec()], 2)
         xa = xp._args(128, 2, False); xa.in_views, xa.x_in, xa.x_out = 1, xx.data_ptr(), xo.data_ptr()
-        shapes = {'xl-8th fwd (d=128, 1 view, 75 M entries)': (xp, xa)}
+        shapes = {('config-4' if sc == 8 else 'xl-8th') + f' fwd (d=128, 1 view, {75 * sc} M entries)': (xp, xa)}
         x, d, V, plan = xx, 128, 1, xplan
     nnz = plan.nnz
     combos = [('interleaved', 0), ('view-major', 1)]
-    if ncu and '--xl' in sys.argv:
+    if ncu and ('--xl' in sys.argv or '--xlfull' in sys.argv):
         combos = combos[:1]
     for what, (prop, args) in shapes.items():
         for mode, vm in combos:
