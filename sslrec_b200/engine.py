@@ -542,6 +542,10 @@ class _PropFn(torch.autograd.Function):
         st = ctx.st
         de0 = st.prop.backward(st)
         nu = st.n_user
+        # token -> grad_fn -> ctx -> state -> token is a reference cycle through the autograd node: break it now instead of leaving
+        # it to the cyclic collector (it would keep the step's tables, and the parameters' gradient accumulators, alive until then)
+        st.token = None
+        ctx.st = None
         return de0[:nu], de0[nu:], None, None, None
 
 

@@ -40,6 +40,11 @@ class GraphedStep:
             model.cal_loss(self.static_batch)
         self.n_seeds = seeds.count - count
         seeds.state, seeds.count = state, count
+        # No autograd graph of earlier eager steps may survive into the capture: a live graph keeps the parameters' AccumulateGrad
+        # nodes -- bound to the stream they were created on, usually the default one -- and a capture that has to synchronise with the
+        # default stream is invalid.  The dry forward above replaced the model's last state; collect what is left.
+        import gc
+        gc.collect()
         seeds.enable_device(dev, capacity=max(8, self.n_seeds))
         optimizer.enable_device_step(dev)
         self.graph = None
