@@ -10,10 +10,8 @@ on ONE GPU, which gives the strong-scaling efficiency of the real config).
 """
 from __future__ import annotations
 
-import os
 import time
 
-import numpy as np
 import torch
 
 import synth_graphs as S

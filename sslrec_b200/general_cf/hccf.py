@@ -105,7 +105,5 @@ class HGNNLayer(nn.Module):
         self.act = nn.LeakyReLU(negative_slope=leaky)
 
     def forward(self, adj, embeds):
-        n = adj.shape[0]
-        empty = adj.new_zeros((0, adj.shape[1]))
-        x = embeds if embeds.is_contiguous() else embeds.contiguous()
-        return E.hyper_layer(torch.cat([x, x.new_zeros((0, x.shape[1]))]), adj, empty, self.slope, E.HyperDrop(), E.HyperDrop())[:n]
+        # one side only: the second side of engine.hyper_layer is empty
+        return E.hyper_layer(embeds, adj, adj.new_zeros((0, adj.shape[1])), self.slope, E.HyperDrop(), E.HyperDrop())

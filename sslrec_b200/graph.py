@@ -7,7 +7,6 @@ SpMM of the backward pass; only an *injected* edge mask needs the reverse-entry 
 from __future__ import annotations
 
 import ctypes as C
-from typing import Optional
 
 import numpy as np
 import torch

@@ -19,7 +19,7 @@ step (run those batches eagerly -- ``GraphedStep.eager`` does, with the same dev
 """
 from __future__ import annotations
 
-from typing import Dict, List, Sequence, Tuple
+from typing import Dict, Sequence, Tuple
 
 import torch
 
