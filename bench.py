@@ -313,6 +313,8 @@ def workload_config(name, n_user, n_item, n_edge, world, mode='single'):
     return {'workload': f'{model} training step on synthetic {graph}-shaped graph', 'model_name': model, 'graph': graph,
             'n_user': n_user, 'n_item': n_item, 'nnz': 2 * n_edge, 'batch': BATCH, 'global_batch': BATCH * (world if mode == 'dp' else 1),
             'dim': hp['embedding_size'], 'layers': hp['layer_num'], 'temperature': hp.get('temperature'), 'parallelism': par,
+            'propagation': 'one prop_kernel launch per layer and direction (2L per step; a layer needs every row of the previous one), layer sum and '
+                           'augmentation fused into the launches',
             'l2': 'no explicit flush: each step touches > 1 GB (3-view activations, gradient sinks, split partials) >> 126 MB L2'}
 
 
@@ -640,7 +642,9 @@ def run_ours(args):
             'e2e': {'value': units * 1e3 / ms_e2e, 'unit': 'steps/s', 'ms_per_step': ms_e2e, 'h2d_bytes_per_step': 3 * BATCH * 8,
                     'd2h_bytes_per_step': 4 * (1 + {'simgcl': 3, 'sgl': 3, 'lightgcn': 2}.get(model_name, 3)),
                     'how': 'sslrec_b200.trainer.Trainer.train_epoch loop: pinned-host batch -> H2D, cal_loss, backward, FusedAdam.step, '
-                           'loss + loss terms copied D2H asynchronously and read one step later (all reads drained inside the timed region)'},
+                           'loss + loss terms copied D2H asynchronously and read one step later (all reads drained inside the timed region)',
+                'strict_sync_value': units * 1e3 / ms_e2e_strict, 'strict_sync_ms_per_step': ms_e2e_strict,
+                'strict_sync_how': 'the reference trainer\'s own loop: blocking loss.item() after cal_loss and float(v) per loss term (trainer.py:66,72)'},
             'e2e_strict_sync': {'value': units * 1e3 / ms_e2e_strict, 'unit': 'steps/s', 'ms_per_step': ms_e2e_strict,
                                 'how': 'the reference trainer\'s blocking reads: loss.item() after cal_loss and float(v) per loss term (trainer.py:66,72)'},
             'e2e_epoch': epoch,
