@@ -34,6 +34,7 @@ struct RowGemmArgs {
     int accumulate;                              // out += instead of out =
     int64_t n_rows;
     int vec;                                     // inputs allow 16-byte loads
+    int vec_out;                                 // out allows 16-byte stores
 };
 
 __device__ __forceinline__ float leaky(float x, float slope) { return x > 0.f ? x : x * slope; }
@@ -140,6 +141,19 @@ __global__ void __launch_bounds__(kT) rowgemm_kernel(RowGemmArgs a) {
         for (int i = 0; i < 4; ++i) {
             const int64_t r = r0 + tr * 4 + i;
             if (r >= a.n_rows) continue;
+            if constexpr (CPT % 4 == 0) {
+                if (a.vec_out && tc * CPT + CPT <= NO) {          // 16-byte stores: CPT contiguous columns of this thread
+#pragma unroll
+                    for (int j = 0; j < CPT; j += 4) {
+                        float4 *o = reinterpret_cast<float4 *>(a.out + r * a.out_stride + tc * CPT + j);
+                        float4 v = make_float4(leaky(acc[i][j] * a.scale, a.slope), leaky(acc[i][j + 1] * a.scale, a.slope),
+                                               leaky(acc[i][j + 2] * a.scale, a.slope), leaky(acc[i][j + 3] * a.scale, a.slope));
+                        if (a.accumulate) ssl::add4(v, *o);
+                        *o = v;
+                    }
+                    continue;
+                }
+            }
 #pragma unroll
             for (int j = 0; j < CPT; ++j) {
                 const int c = tc * CPT + j;
@@ -374,7 +388,7 @@ extern "C" int ssl_rowgemm(const float *in1, int64_t in1_stride, int32_t k1, con
     auto al16 = [](const void *p, int64_t stride) { return p == nullptr || ((reinterpret_cast<uintptr_t>(p) & 15) == 0 && stride % 4 == 0); };
     const int vec = (k1 % 4 == 0 && (in2 == nullptr || k2 % 4 == 0) && al16(in1, in1_stride) && al16(in2, in2_stride) && al16(pre_ref, pre_stride)) ? 1 : 0;
     RowGemmArgs a{in1, in1_stride, k1, m1, m1_trans, in2, in2_stride, in2 ? k2 : 0, m2, m2_trans, pre_ref, pre_stride, pre_slope, out, out_stride, n_out,
-                  scale, slope, accumulate, n_rows, vec};
+                  scale, slope, accumulate, n_rows, vec, al16(out, out_stride) ? 1 : 0};
     cudaStream_t st = (cudaStream_t)stream;
     switch (round_n(n_out)) {
         case 1: return launch_rowgemm<1>(a, st);
