@@ -82,9 +82,13 @@ def _time_steps(model, opt, batches, steps, warmup, dist, dev):
             dist.barrier()
         torch.cuda.synchronize()
 
+    first = None
     for i in range(warmup):
-        step(i)
+        l = step(i)
+        if i == 0:
+            first = l
     barrier()
+    first_loss = float(first.item()) if first is not None else None          # the loss of the very first step: same init, same batch on 1 and on N GPUs
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(steps):
@@ -122,6 +126,7 @@ def _time_steps(model, opt, batches, steps, warmup, dist, dev):
     engine.TIMER = None
     loss = float(step(0).item())
     summ['e2e_ms_per_step'] = ms_e2e
+    summ['first_loss'] = first_loss
     return ms, summ, loss
 
 
@@ -134,7 +139,7 @@ def _single_gpu(keys, n_user, n_item, dev, steps, warmup):
     del model, opt, handler, batches
     torch.cuda.empty_cache()
     return dict(ms_per_step=ms, e2e_ms_per_step=summ['e2e_ms_per_step'], spmm_ms=summ.get('prop_fwd', {}).get('ms', 0.0) + summ.get('prop_bwd', {}).get('ms', 0.0),
-                spmm_launches=summ.get('prop_fwd', {}).get('launches', 0) + summ.get('prop_bwd', {}).get('launches', 0), nnz=nnz, max_row_nnz=stats['max_row_nnz'], loss=loss)
+                spmm_launches=summ.get('prop_fwd', {}).get('launches', 0) + summ.get('prop_bwd', {}).get('launches', 0), nnz=nnz, max_row_nnz=stats['max_row_nnz'], loss=loss, first_loss=summ['first_loss'])
 
 
 def leg(dist, rank, world, dev, steps=5, warmup=2, full=False, baselines=True, log=lambda *a: None):
@@ -188,7 +193,7 @@ def leg(dist, rank, world, dev, steps=5, warmup=2, full=False, baselines=True, l
                     'how': 'spmm_ms = CUDA-event time of the 2L propagation launches (the peer stores of the fused all-gather travel inside them); '
                            'exchange_ms = what is left of the exchange after the launch (cross-GPU barrier; with the nccl transport the all_gather itself); '
                            'nvlink_GBps = bytes this rank stored into its peers per step / (spmm_ms + adam_ms)',
-                    'loss': loss, 'steps': steps, 'warmup': warmup})
+                    'loss': loss, 'first_loss': summ['first_loss'], 'steps': steps, 'warmup': warmup})
         rec['multicast'] = bool(comm._tables and next(iter(comm._tables.values())).mc_ptr)
         del model, opt, handler, batches
         comm._tables.clear()                                  # the shared tables (6.1 GB each at config 4) go before rank 0's one-GPU baselines
@@ -213,6 +218,19 @@ def leg(dist, rank, world, dev, steps=5, warmup=2, full=False, baselines=True, l
                 except Exception as e:      # noqa: BLE001 -- e.g. out of memory on a shared box: the sharded numbers stand without it
                     base['one_gpu_config4'] = {'error': repr(e)[:300]}
                 del kf
+            # 1-vs-N equality on the SAME graph: the first step's loss (same seed -> same initial table, same first batch)
+            if world > 1 and 'first_loss' in rec:
+                same = base.get('one_gpu_config4') if scale == 8 else None
+                if same is None or 'first_loss' not in same:
+                    try:
+                        same = _single_gpu(keys, n_user, n_item, dev, 1, 1)
+                        base['one_gpu_same_graph'] = {'first_loss': same['first_loss'], 'ms_per_step': same['ms_per_step']}
+                    except Exception as e:      # noqa: BLE001
+                        same = None
+                        base['one_gpu_same_graph'] = {'error': repr(e)[:300]}
+                if same is not None and same.get('first_loss') is not None:
+                    rec['first_loss_one_gpu'] = same['first_loss']
+                    rec['first_loss_abs_diff'] = abs(rec['first_loss'] - same['first_loss'])
         if world > 1:
             dist.barrier()
         if rank == 0:
