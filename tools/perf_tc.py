@@ -14,7 +14,7 @@ def prep(x, n, d, alpha):
 def run(nr, nc, d, tc, reps=10, split=None):
     g = torch.Generator().manual_seed(0)
     R = prep(torch.randn(nr, d, generator=g).cuda(), nr, d, 7.2); C = prep(torch.randn(nc, d, generator=g).cuda(), nc, d, 1.0)
-    ns = split or choose_split((nr + 127) // 128, C[6] // 64, slots=148 if tc else 296)
+    ns = split or choose_split((nr + 127) // 128, C[6] // 64, slots=148 if tc else 296, prefer_few=tc)
     rs, o = torch.zeros(ns, nr, **f), torch.zeros(ns, nr, d, **f)
     s = torch.cuda.current_stream().cuda_stream
     def call():
@@ -29,6 +29,15 @@ def run(nr, nc, d, tc, reps=10, split=None):
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
     print(f'nr={nr} nc={nc} d={d} tc={tc} split={ns}: {ms:.3f} ms  {4.0 * nr * nc * d / ms / 1e9:.1f} TFLOP/s(fp32-equivalent)', flush=True)
+if len(sys.argv) > 1 and sys.argv[1] == 'sweep':
+    # n_split sweep at the bench's shapes: forward role (anchors resident, table streamed) and backward role (table resident)
+    for nr, nc, splits in ((4096, 76469, (5, 7, 9, 14, 18, 23)), (4096, 83761, (5, 7, 9, 14, 18, 23)), (76469, 4096, (1, 2, 3, 4, 6, 8)), (83761, 4096, (1, 2, 3, 4, 6, 8)),
+                           (4096, 25557, (3, 5, 9, 14)), (25557, 4096, (1, 2, 3, 4, 8))):
+        print('heuristic:', end=' ')
+        run(nr, nc, 64, True, reps=20)
+        for sp in splits:
+            run(nr, nc, 64, True, reps=20, split=sp)
+    sys.exit(0)
 quick = len(sys.argv) > 1
 for tc in ((True,) if quick else (True, False)):
     run(4096, 83761, 64, tc)
