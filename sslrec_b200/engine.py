@@ -671,19 +671,26 @@ def bpr_loss_sum(users: Rows, items: Rows, ancs, poss, negs) -> torch.Tensor:
 
 
 def choose_split(n_rtiles: int, n_ctiles: int, slots: int = 2 * 148, prefer_few: bool = False) -> int:
-    """Number of chunks the streamed operand is cut into so that n_rtiles * n_split CTAs fill whole waves of the
-    resident-CTA slots (2 per SM for the FFMA kernel at dim <= 64, 1 per SM for the tcgen05 kernel) with every
-    CTA keeping >= 4 tiles.  ``prefer_few``: among splits within 5 % of the best wave efficiency take the
-    smallest -- the tcgen05 kernel pays a resident-tile load + pipeline fill per CTA (measured 0.380 ms at 37
-    splits vs 0.339 ms at 9 for the bench's forward shape)."""
+    """Number of chunks the streamed operand is cut into: n_rtiles * n_split CTAs on ``slots`` resident-CTA slots (2 per SM for
+    the FFMA kernel at dim <= 64, 1 per SM for the tcgen05 kernel), every CTA keeping >= 4 tiles.
+
+    ``prefer_few`` (the tcgen05 kernel): minimise  waves(s) * (tiles_per_cta(s) + c)  with c = 5.5 tile-times of per-CTA overhead
+    (resident-tile load, TMEM allocation, pipeline fill, O read-out), fitted to a sweep on B200 at the bench shapes (tools/perf_tc.py
+    sweep, profiles/r02_ncu_kernels.md): forward role 32 row tiles x 1195 tiles -> 9 (0.314 ms; 5: 0.518, 14: 0.391); backward role
+    598 row tiles x 64 tiles -> 2 (0.357 ms; the pure wave-efficiency rule picked 4: 0.390).
+    Otherwise: the split with the best wave efficiency (FFMA kernel)."""
     max_split = max(1, min(n_ctiles // 4 if n_ctiles >= 4 else 1, 64))
+    if prefer_few:
+        best, best_cost = 1, None
+        for s in range(1, max_split + 1):
+            cost = math.ceil(n_rtiles * s / slots) * (math.ceil(n_ctiles / s) + 5.5)
+            if best_cost is None or cost < best_cost - 1e-9:
+                best, best_cost = s, cost
+        return best
     effs = []
     for s in range(1, max_split + 1):
         ctas = n_rtiles * s
         effs.append((ctas / (math.ceil(ctas / slots) * slots), s))
-    best_eff = max(e for e, _ in effs)
-    if prefer_few:
-        return min(s for e, s in effs if e >= best_eff - 0.05)
     return max(effs, key=lambda t: (round(t[0], 9), -t[1]))[1]
 
 
