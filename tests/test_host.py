@@ -87,6 +87,10 @@ def test_choose_split_fills_waves():
     assert choose_split(32, 1) == 1
     s = choose_split(655, 64)
     assert 1 <= s <= 16 and (655 * s) / (296 * -(-655 * s // 296)) > 0.95
+    # the tcgen05 kernel (1 CTA per SM): waves x (tiles per CTA + per-CTA overhead), fitted to the B200 sweep (tools/perf_tc.py sweep)
+    assert choose_split(32, 1195, slots=148, prefer_few=True) == 9          # forward role at the amazon shape: measured optimum
+    assert choose_split(598, 64, slots=148, prefer_few=True) == 2           # backward role: measured optimum (the wave-efficiency rule said 4)
+    assert choose_split(200, 64, slots=148, prefer_few=True) == 2 and choose_split(1, 1, slots=148, prefer_few=True) == 1
 
 
 def test_device_side_components_fail_loudly_without_cuda():
