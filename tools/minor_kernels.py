@@ -1,0 +1,85 @@
+"""Evaluation-side and clustering kernels at the amazon shape, outside any model: ``ssl_predict_mask`` (full_predict + _mask_predict
+with the mask taken from the device CSR), ``ssl_topk`` (k = 40) and ``ssl_kmeans_iter`` (NCL, K = 50).  Live CUDA-event timings
+as one JSON line; with ``--ncu`` only the launches (for ``ncu --set full -k regex:"predict_mask|topk_kernel|kmeans"``).
+
+    python tools/minor_kernels.py [--ncu]
+"""
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from sslrec_b200._lib import check, lib          # noqa: E402
+from sslrec_b200.kmeans import KMeansClustering  # noqa: E402
+from sslrec_b200.trainer import topk             # noqa: E402
+
+U, I, D, BT, DEG, K_TOP, K_CLUSTER = 76469, 83761, 64, 1024, 12, 40, 50
+
+
+def main():
+    ncu = '--ncu' in sys.argv
+    dev = torch.device('cuda', 0)
+    torch.cuda.set_device(dev)
+    g = torch.Generator(device=dev).manual_seed(1)
+    ue = torch.randn(U, D, device=dev, generator=g) * 0.1
+    ie = torch.randn(I, D, device=dev, generator=g) * 0.1
+    users = torch.randint(0, U, (BT,), device=dev, generator=g)
+    # training CSR: DEG distinct items per user, sorted within the row (what BaseModel._train_csr builds from trn_mat)
+    u = torch.arange(U, device=dev).unsqueeze(1)
+    j = torch.arange(DEG, device=dev).unsqueeze(0)
+    cols = ((u * 7 + j * 6997) % I).sort(1).values.to(torch.int32).reshape(-1).contiguous()
+    rowptr = (torch.arange(U + 1, device=dev) * DEG).to(torch.int32)
+    preds = torch.empty(BT, I, device=dev)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+
+    def predict():
+        check(lib.ssl_predict_mask(ue.data_ptr(), ue.stride(0), ie.data_ptr(), ie.stride(0), users.data_ptr(), BT, I, D,
+                                   None, rowptr.data_ptr(), cols.data_ptr(), preds.data_ptr(), stream), 'ssl_predict_mask')
+
+    def timed(fn, reps):
+        fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    if ncu:
+        for _ in range(3):
+            predict()
+            topk(preds, K_TOP)
+        KMeansClustering(K_CLUSTER, D, iters=4, check_every=100)(ue)
+        torch.cuda.synchronize()
+        return
+    out = {'shape': dict(users=U, items=I, dim=D, eval_batch=BT, k=K_TOP, clusters=K_CLUSTER)}
+    ms = timed(predict, 20)
+    out['predict_mask'] = {'ms': ms, 'tflops_fp32': 2.0 * BT * I * D / ms / 1e9, 'write_GBps': 4.0 * BT * I / ms / 1e6}
+    idx = topk(preds, K_TOP)
+    ref = torch.topk(preds, K_TOP).indices
+    out['topk_matches_torch'] = float((idx == ref).float().mean().item())
+    ms = timed(lambda: topk(preds, K_TOP), 20)
+    out['topk'] = {'ms': ms, 'read_GBps_one_pass': 4.0 * BT * I / ms / 1e6}
+    ms_t = timed(lambda: torch.topk(preds, K_TOP), 20)
+    out['torch_topk_ms'] = ms_t
+    km = KMeansClustering(K_CLUSTER, D, iters=32, check_every=1000)
+    km(ue)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    km(ue)
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / km.last_iters
+    out['kmeans_iter'] = {'ms': ms, 'iters': km.last_iters, 'tflops_fp32': 3.0 * U * K_CLUSTER * D / ms / 1e9, 'table_read_GBps': 4.0 * U * D / ms / 1e6}
+    print(json.dumps(out), flush=True)
+
+
+if __name__ == '__main__':
+    main()
