@@ -541,6 +541,18 @@ def run_ours(args):
             except Exception as e:      # noqa: BLE001 -- an extra record must never cost the bench line
                 graphed = {'error': repr(e)[:400]}
 
+        # ---- the evaluation-side kernels (full_predict + _mask_predict through both of its kernels, top-k, one k-means iteration) at the
+        # amazon shape, in their own process (tools/minor_kernels.py): an extra record, never allowed to cost the bench line ----
+        eval_kernels = None
+        if world == 1 and not args.no_eval_kernels and args.workload == 'simgcl-amazon':
+            try:
+                env = {k: v for k, v in os.environ.items() if k not in ('RANK', 'LOCAL_RANK', 'WORLD_SIZE')}
+                r = subprocess.run([sys.executable, os.path.join(ROOT, 'tools', 'minor_kernels.py')], capture_output=True, text=True, timeout=240, env=env)
+                lines = [ln for ln in r.stdout.strip().splitlines() if ln.startswith('{')]
+                eval_kernels = json.loads(lines[-1]) if lines else {'error': (r.stderr or 'no output')[-400:]}
+            except Exception as e:      # noqa: BLE001
+                eval_kernels = {'error': repr(e)[:400]}
+
         peaks, peak_kind = measured_peaks()
         N, nnz, d = n_user + n_item, 2 * len(rows), hp['embedding_size']
         L = hp['layer_num']
@@ -650,7 +662,7 @@ def run_ours(args):
             'e2e_epoch': epoch,
             'gpu_launches': launches, 'gpu_launches_per_step': launches / K,
             'embeddings_propagated_per_sec': emb_per_step * value,
-            'roofline': roofline, 'roofline_infonce': roofline_nce, 'cpu_baseline': cpu, 'row_shard': None, 'cuda_graph': graphed,
+            'roofline': roofline, 'roofline_infonce': roofline_nce, 'cpu_baseline': cpu, 'row_shard': None, 'cuda_graph': graphed, 'eval_kernels': eval_kernels,
             'roofline_note': 'roofline = the SpMM BASELINE.json names (HBM-bound); roofline_infonce = the kernel with the largest share of this '
                              'step (tensor-bound contraction); both carry share_of_step',
             'clocks': clocks, 'clocks_e2e': clocks_e2e, 'kernel_ms_per_step': {k: v['ms'] / K for k, v in summ.items()}, 'profiled_ms_per_step': prof_ms,
@@ -834,6 +846,7 @@ def main():
     ap.add_argument('--workload', default='simgcl-amazon', choices=sorted(WORKLOADS))
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-cuda-graph', action='store_true', help='skip the cuda_graph record (e.g. under a profiler)')
+    ap.add_argument('--no-eval-kernels', action='store_true', help='skip the eval_kernels record (predict / top-k / k-means timings in a subprocess)')
     ap.add_argument('--cpu-budget', type=float, default=170.0, help='--impl reference: wall-clock budget of the timed CPU steps (s)')
     ap.add_argument('--cpu-csr', action='store_true', help='--impl reference: adjacency converted with to_sparse_csr() ("tuned CPU")')
     ap.add_argument('--row-shard', default='auto', choices=['auto', 'on', 'off'],

@@ -52,7 +52,9 @@ SSL_API const char *ssl_last_error(void);
 SSL_API int64_t ssl_launch_count(void);
 /* process-wide switches for tests and A/B profiling (value 0 / 1):
  *   "prop_view_major"  propagation with grid.y = view and one accumulator per thread: DRAM traffic at 1.03x compulsory instead of
- *                      1.3x, but 25-40 % slower on B200 (profiles/r02_prop_variants.md); default 0 */
+ *                      1.3x, but 25-40 % slower on B200 (profiles/r02_prop_variants.md); default 0
+ *   "predict_tiled"    ssl_predict_mask as a register-tiled product (128 x 128 score tiles, csrc/predict_tile.cuh); 0 selects the
+ *                      round-1 warp-per-item kernel (4 % of the FFMA rate, profiles/r02_ncu_kernels.md), kept as the cross-check; default 1 */
 SSL_API int ssl_set_option(const char *name, int64_t value);
 
 /* ------------------------------------------------------------------------------------------
@@ -283,7 +285,8 @@ SSL_API int ssl_adam_step_dev(float *p, float *const *p_peers, int32_t n_peers, 
  * consumes it (metrics.py:108).
  * ssl_predict_mask: preds[b, i] = (U[users[b]] . I[i]) * (1 - M[b,i]) - 1e8 * M[b,i]; the mask is
  *   either the dense int64 [n_b, n_item] tensor the reference passes (mask_dense) or, when that
- *   is NULL, the training CSR (trn_rowptr int32 [n_user+1], trn_cols int32) read on device.
+ *   is NULL, the training CSR (trn_rowptr int32 [n_user+1], trn_cols int32) read on device.  Every score is one
+ *   sequential fp32 FMA chain over k = 0 .. dim-1; masked positions read exactly -1e8.
  * ssl_topk: the k largest entries of every row, descending, ties broken by the lower index.
  * ------------------------------------------------------------------------------------------ */
 SSL_API int ssl_predict_mask(const float *users_tab, int64_t u_stride, const float *items_tab, int64_t i_stride,

@@ -18,6 +18,7 @@ void set_error(const char *fmt, ...) {
     va_end(ap);
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+int g_predict_tiled = 1;
 }  // namespace ssl
 
 extern "C" int ssl_version(void) { return 100; }

@@ -10,6 +10,7 @@ namespace ssl {
 
 void set_error(const char *fmt, ...);
 void count_launch(int n = 1);
+extern int g_predict_tiled;   // ssl_set_option("predict_tiled", v): 1 (default) = predict_tile_kernel, 0 = the warp-per-item kernel
 
 #define SSL_CHECK_ARG(cond, ...)                \
     do {                                        \

@@ -4,6 +4,7 @@
 #include <math_constants.h>
 
 #include "common.cuh"
+#include "predict_tile.cuh"
 
 namespace {
 
@@ -603,6 +604,15 @@ extern "C" int ssl_predict_mask(const float *users_tab, int64_t u_stride, const 
     SSL_CHECK_ARG(dim >= 1 && dim <= SSL_MAX_DIM, "ssl_predict_mask: dim %d out of range", dim);
     SSL_CHECK_ARG(n_b <= 65535, "ssl_predict_mask: at most 65535 users per call");
     if (n_b == 0 || n_item == 0) return SSL_OK;
+    if (ssl::g_predict_tiled) {      // default: 128 x 128 score tiles, every item row read once per 128 users (predict_tile.cuh)
+        namespace P = ssl_predict;
+        dim3 grid((unsigned)((n_item + P::TN - 1) / P::TN), (unsigned)((n_b + P::TM - 1) / P::TM));
+        P::predict_tile_kernel<<<grid, P::NT, 0, STREAM>>>(users_tab, u_stride, items_tab, i_stride, users, n_b, n_item, dim, mask_dense, trn_rowptr,
+                                                          trn_cols, preds);
+        SSL_LAUNCH_CHECK("predict_tile_kernel");
+        return SSL_OK;
+    }
+    // ssl_set_option("predict_tiled", 0): the round-1 kernel (one warp per (user, item) dot product), kept as the cross-check
     dim3 grid((unsigned)((n_item + 1023) / 1024), (unsigned)n_b);
     predict_mask_kernel<<<grid, 256, 0, STREAM>>>(users_tab, u_stride, items_tab, i_stride, users, n_item, dim, mask_dense, trn_rowptr, trn_cols, preds);
     SSL_LAUNCH_CHECK("predict_mask_kernel");

@@ -392,6 +392,10 @@ extern "C" int ssl_set_option(const char *name, int64_t value) {
         g_view_major = value == 0;
         return SSL_OK;
     }
+    if (n == "predict_tiled") {             // 0: the warp-per-item score kernel instead of the tiled one (ssl_predict_mask)
+        ssl::g_predict_tiled = value != 0;
+        return SSL_OK;
+    }
     ssl::set_error("ssl_set_option: unknown option '%s'", name);
     return SSL_E_ARG;
 }

@@ -194,6 +194,57 @@ def test_spec_nodes_infonce_and_bpr_dense():
         H.close(x.grad, y.grad, 1e-5, 1e-6, 'bpr grad')
 
 
+def _predict_case(n_b, n_item, dim, view, mode, dev):
+    """Seeded inputs of one ssl_predict_mask call: (user table view, item table, users, dense mask | None, rowptr | None, cols | None,
+    float64 scores, bool positions that must read -1e8)."""
+    g = torch.Generator().manual_seed(11)
+    n_user = n_b // 2 + 3                                      # users repeat inside the batch
+    V = 3 if view else 1
+    ubase = (torch.randn(n_user, V, dim, generator=g) * 0.2).to(dev)
+    ibase = (torch.randn(n_item, dim, generator=g) * 0.2).to(dev)
+    ut = ubase[:, V - 1, :]                                    # view: the last view of an interleaved [n, 3, d] table (row stride 3 d)
+    users = torch.randint(0, n_user, (n_b,), generator=g)
+    keep = torch.rand(n_user, n_item, generator=g) < 0.2       # the users' training positives
+    mask = rowptr = cols = None
+    if mode == 'dense':
+        mask = keep[users].long().contiguous().to(dev)
+    elif mode == 'csr':
+        rowptr = torch.cat([torch.zeros(1, dtype=torch.long), keep.sum(1).cumsum(0)]).int().to(dev)
+        cols = keep.nonzero()[:, 1].int()                      # row-major: ascending inside a row
+        cols = (cols if cols.numel() else torch.zeros(1, dtype=torch.int32)).to(dev)
+    ref = ut.cpu().double()[users] @ ibase.cpu().double().T
+    masked = keep[users] if mode != 'none' else torch.zeros(n_b, n_item, dtype=torch.bool)
+    return ut, ibase, users.to(dev), mask, rowptr, cols, ref, masked
+
+
+@pytest.mark.parametrize('n_b,n_item,dim,view', [(1, 1, 4, False), (130, 300, 64, False), (257, 1029, 48, True), (1024, 5003, 128, False)])
+@pytest.mark.parametrize('mode', ['none', 'dense', 'csr'])
+def test_predict_tiled_kernel_matches_float64_and_the_warp_kernel(n_b, n_item, dim, view, mode):
+    """ssl_predict_mask through both of its kernels (the 128 x 128 tiled product, default, and the round-1 warp-per-item kernel,
+    ssl_set_option("predict_tiled", 0)): scores against float64, masked positions exactly -1e8, ragged tiles, strided table view."""
+    from sslrec_b200._lib import check, lib
+    dev = torch.device('cuda')
+    ut, ibase, users, mask, rowptr, cols, ref, masked = _predict_case(n_b, n_item, dim, view, mode, dev)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+
+    def run(tiled):
+        preds = torch.full((n_b, n_item), -7.0, device=dev)
+        check(lib.ssl_set_option(b'predict_tiled', int(tiled)), 'ssl_set_option')
+        try:
+            check(lib.ssl_predict_mask(ut.data_ptr(), ut.stride(0), ibase.data_ptr(), ibase.stride(0), users.data_ptr(), n_b, n_item, dim,
+                                       None if mask is None else mask.data_ptr(), None if rowptr is None else rowptr.data_ptr(),
+                                       None if cols is None else cols.data_ptr(), preds.data_ptr(), stream), 'ssl_predict_mask')
+        finally:
+            check(lib.ssl_set_option(b'predict_tiled', 1), 'ssl_set_option')
+        torch.cuda.synchronize()
+        return preds.cpu()
+
+    for name, got in (('tiled', run(True)), ('warp', run(False))):
+        assert torch.equal(got[masked], torch.full_like(got[masked], -1e8)), name
+        err = (got[~masked].double() - ref[~masked]).abs().max().item() if (~masked).any() else 0.0
+        assert err <= 5e-6, (name, err)
+
+
 def test_topk_exact_with_ties():
     from sslrec_b200.trainer import topk
     g = torch.Generator().manual_seed(8)

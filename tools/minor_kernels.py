@@ -1,5 +1,5 @@
 """Evaluation-side and clustering kernels at the amazon shape, outside any model: ``ssl_predict_mask`` (full_predict + _mask_predict
-with the mask taken from the device CSR), ``ssl_topk`` (k = 40) and ``ssl_kmeans_iter`` (NCL, K = 50).  Live CUDA-event timings
+with the mask taken from the device CSR; both of its kernels), ``ssl_topk`` (k = 40) and ``ssl_kmeans_iter`` (NCL, K = 50).  Live CUDA-event timings
 as one JSON line; with ``--ncu`` only the launches (for ``ncu --set full -k regex:"predict_mask|topk_kernel|kmeans"``).
 
     python tools/minor_kernels.py [--ncu]
@@ -58,9 +58,24 @@ def main():
         KMeansClustering(K_CLUSTER, D, iters=4, check_every=100)(ue)
         torch.cuda.synchronize()
         return
-    out = {'shape': dict(users=U, items=I, dim=D, eval_batch=BT, k=K_TOP, clusters=K_CLUSTER)}
-    ms = timed(predict, 20)
-    out['predict_mask'] = {'ms': ms, 'tflops_fp32': 2.0 * BT * I * D / ms / 1e9, 'write_GBps': 4.0 * BT * I / ms / 1e6}
+    out = {'shape': dict(users=U, items=I, dim=D, eval_batch=BT, k=K_TOP, clusters=K_CLUSTER),
+           'how': 'CUDA events around 20 back-to-back launches after one warm-up launch; amazon shape, random tables, training CSR of 12 items per user'}
+    # both score kernels behind ssl_predict_mask: the 128 x 128 tiled product (default) and the round-1 warp-per-item kernel
+    res = {}
+    for key, flag in (('predict_mask_warp_per_item', 0), ('predict_mask', 1)):
+        check(lib.ssl_set_option(b'predict_tiled', flag), 'ssl_set_option')
+        ms = timed(predict, 20)
+        res[key] = preds.clone()
+        out[key] = {'kernel': 'predict_tile_kernel' if flag else 'predict_mask_kernel', 'ms': ms, 'tflops_fp32': 2.0 * BT * I * D / ms / 1e9,
+                    'write_GBps': 4.0 * BT * I / ms / 1e6, 'write_roofline_ms': 4.0 * BT * I / 6490.5e6}
+    a, b = res['predict_mask'], res['predict_mask_warp_per_item']
+    ref = (ue[users].double() @ ie.double().T)
+    unmasked = a > -1e7
+    out['predict_parity'] = {'masked_positions_equal': bool(torch.equal(a <= -1e7, b <= -1e7)), 'masked_per_row': float((~unmasked).sum().item()) / BT,
+                             'tiled_vs_float64_max_abs': float((a.double() - ref)[unmasked].abs().max().item()),
+                             'warp_vs_float64_max_abs': float((b.double() - ref)[b > -1e7].abs().max().item()),
+                             'top40_identical_between_kernels': float((topk(a, K_TOP) == topk(b, K_TOP)).float().mean().item())}
+    del res, a, b, ref, unmasked
     idx = topk(preds, K_TOP)
     ref = torch.topk(preds, K_TOP).indices
     out['topk_matches_torch'] = float((idx == ref).float().mean().item())
