@@ -194,37 +194,82 @@ class Trainer(object):
         unknown = [m for m in metrics if m not in ('recall', 'ndcg', 'precision', 'mrr')]
         if unknown:
             raise ValueError(f'unknown test metrics {unknown} (metrics.py knows recall, ndcg, precision, mrr)')
-        result = {m: np.zeros(len(ks)) for m in metrics}
+        per_user = {m: [] for m in metrics}
         ds = loader.dataset
         n_users = len(ds.test_users)
+        ptr, flat = truth_csr(ds)
         seen = 0
         for tem in loader:
             if not isinstance(tem, (list, tuple)):
                 tem = [tem]
-            users = tem[0].numpy().tolist()
+            users = tem[0].numpy().astype(np.int64)
             batch_data = list(map(lambda x: x.long().to(configs['device']), tem))
             if len(batch_data) == 1:
                 batch_data.append('train')                   # dataset built with dense_mask=False: mask from the device CSR
             preds = model.full_predict(batch_data)
             seen += preds.shape[0]
             top = topk(preds, max(ks)).cpu().numpy()
-            for bi, u in enumerate(users):
-                truth = ds.user_pos_lists[u]
-                hit = np.isin(top[bi], truth).astype(np.float64)
-                for ki, k in enumerate(ks):
-                    if 'recall' in result:
-                        result['recall'][ki] += hit[:k].sum() / len(truth) / n_users
-                    if 'ndcg' in result:
-                        idcg = (1.0 / np.log2(np.arange(2, min(k, len(truth)) + 2))).sum()
-                        result['ndcg'][ki] += (hit[:k] / np.log2(np.arange(2, k + 2))).sum() / idcg / n_users
-                    if 'precision' in result:
-                        result['precision'][ki] += hit[:k].sum() / k / n_users
-                    if 'mrr' in result:                      # metrics.py:24-29: sum of hit / rank over the top k
-                        result['mrr'][ki] += (hit[:k] / np.arange(1, k + 1)).sum() / n_users
+            rows = batch_metric_rows(top, users, ptr, flat, ks, metrics)
+            for m in metrics:
+                per_user[m].append(rows[m])
         assert seen == n_users, 'evaluation did not cover every test user (metrics.py:113)'
+        # one sum over all users in loader order: the result does not depend on how the users were batched
+        result = {m: (np.concatenate(per_user[m]).sum(0) / n_users if per_user[m] else np.zeros(len(ks))) for m in metrics}
         if self.logger is not None:
             self.logger.log_eval(result, ks, data_type=data_type or 'Validation set', epoch_idx=epoch_idx)
         return result
+
+
+def truth_csr(ds):
+    """The held-out positives of an AllRankTstData (``user_pos_lists``, datasets_general_cf.py:52-58) as one flat CSR (ptr int64
+    [n_user + 1], items int64), built once per dataset."""
+    cached = getattr(ds, '_truth_csr', None)
+    if cached is None:
+        import itertools
+        lists = ds.user_pos_lists
+        lens = np.fromiter((len(x) for x in lists), dtype=np.int64, count=len(lists))
+        ptr = np.zeros(len(lists) + 1, dtype=np.int64)
+        np.cumsum(lens, out=ptr[1:])
+        flat = np.fromiter(itertools.chain.from_iterable(lists), dtype=np.int64, count=int(ptr[-1]))
+        cached = ds._truth_csr = (ptr, flat)
+    return cached
+
+
+def batch_metric_rows(top, users, ptr, flat, ks, metrics):
+    """recall / ndcg / precision / mrr of metrics.py:11-45 for one evaluation batch, one value per row and cut-off, without the
+    per-user Python loop (82 us per user on the host: 6 s per amazon-sized evaluation against 0.1-0.4 s of GPU work).
+
+    top   [n, max(ks)] item ids, best first (the top-k of full_predict's masked scores)
+    users [n] the rows' user ids; (ptr, flat): ``truth_csr`` of the held-out positives
+    -> {metric: float64 [n, len(ks)]}; the caller sums over all test users and divides by their number (metrics.py:122-124)."""
+    top = np.asarray(top, dtype=np.int64)
+    users = np.asarray(users, dtype=np.int64)
+    n, kmax = top.shape
+    lens = ptr[users + 1] - ptr[users]
+    total = int(lens.sum())
+    # (row, item) keys of the batch's ground truth; a hit is a top-k entry whose key is among them (np.isin per row in the loop form)
+    first = np.cumsum(lens) - lens
+    within = np.arange(total, dtype=np.int64) - np.repeat(first, lens)
+    truth_items = flat[np.repeat(ptr[users], lens) + within]
+    base = int(max(top.max(initial=0), truth_items.max(initial=0))) + 1
+    truth_keys = np.repeat(np.arange(n, dtype=np.int64), lens) * base + truth_items
+    hit = np.isin(np.arange(n, dtype=np.int64)[:, None] * base + top, truth_keys).astype(np.float64)
+    disc = 1.0 / np.log2(np.arange(2, kmax + 2))              # 1 / log2(rank + 1)
+    ideal = np.cumsum(disc)                                   # idcg of a user with j + 1 positives at a cut-off >= j + 1
+    denom = np.maximum(lens, 1)
+    out = {m: np.zeros((n, len(ks))) for m in metrics}
+    for ki, k in enumerate(ks):
+        h = hit[:, :k]
+        right = h.sum(1)
+        if 'recall' in out:
+            out['recall'][:, ki] = right / denom
+        if 'precision' in out:
+            out['precision'][:, ki] = right / k
+        if 'ndcg' in out:
+            out['ndcg'][:, ki] = (h * disc[:k]).sum(1) / ideal[np.minimum(k, denom) - 1]
+        if 'mrr' in out:                                      # metrics.py:24-29: sum of hit / rank over the top k
+            out['mrr'][:, ki] = (h / np.arange(1, k + 1)).sum(1)
+    return out
 
 
 class LossReader:

@@ -202,3 +202,42 @@ def test_trainer_early_stop_restores_best_state_tests_and_saves(tmp_path, monkey
     import pytest
     with pytest.raises(ValueError):
         Trainer(types.SimpleNamespace(test_dataloader=[])).evaluate(Model())
+
+
+def test_vectorised_evaluation_metrics_match_the_per_user_loop_and_do_not_depend_on_batching():
+    """trainer.batch_metric_rows (recall / ndcg / precision / mrr, metrics.py:11-45) against the per-user loop form of the same
+    formulas: truth lists with duplicates and with more entries than the cut-off, several hits per row; summed over all users in
+    loader order the result is bit-identical for any batch size."""
+    from sslrec_b200.trainer import batch_metric_rows, truth_csr
+    rs = np.random.RandomState(0)
+    n_users, n_item, kmax, ks = 700, 900, 40, [10, 20, 40]
+    top = np.stack([rs.permutation(n_item)[:kmax] for _ in range(n_users)])
+    truths = [rs.choice(n_item, size=rs.randint(1, 60), replace=True).tolist() for _ in range(n_users)]
+    for u in range(n_users):
+        for _ in range(rs.randint(0, 4)):
+            top[u, rs.randint(0, kmax)] = truths[u][rs.randint(len(truths[u]))]
+    mets = ('recall', 'ndcg', 'precision', 'mrr')
+    want = {m: np.zeros(len(ks)) for m in mets}
+    for u in range(n_users):
+        hit = np.isin(top[u], truths[u]).astype(np.float64)
+        for ki, k in enumerate(ks):
+            want['recall'][ki] += hit[:k].sum() / len(truths[u]) / n_users
+            idcg = (1.0 / np.log2(np.arange(2, min(k, len(truths[u])) + 2))).sum()
+            want['ndcg'][ki] += (hit[:k] / np.log2(np.arange(2, k + 2))).sum() / idcg / n_users
+            want['precision'][ki] += hit[:k].sum() / k / n_users
+            want['mrr'][ki] += (hit[:k] / np.arange(1, k + 1)).sum() / n_users
+    ptr, flat = truth_csr(types.SimpleNamespace(user_pos_lists=truths))
+    order = rs.permutation(n_users)                              # loaders serve test_users, not 0..n-1
+
+    def run(batch):
+        per = {m: [] for m in mets}
+        for lo in range(0, n_users, batch):
+            rows = batch_metric_rows(top[order[lo:lo + batch]], order[lo:lo + batch], ptr, flat, ks, mets)
+            for m in mets:
+                per[m].append(rows[m])
+        return {m: np.concatenate(per[m]).sum(0) / n_users for m in mets}
+    a, b = run(1024), run(96)
+    for m in mets:
+        assert np.abs(a[m] - want[m]).max() < 1e-13, m
+        assert np.array_equal(a[m], b[m]), m
+    assert want['recall'][0] > 0 and want['mrr'][2] > 0
