@@ -508,24 +508,60 @@ def run_ours(args):
         # ---- one real epoch through Trainer.train_epoch (sample_negs + loader + loop), device loader vs host DataLoader ----
         epoch = None
         if world == 1 and model_name != 'ncl' and len(rows) // BATCH <= 1000:
-            import types
-            from sslrec_b200.data_handler import DeviceLoader, DeviceTrnData
-            from sslrec_b200.trainer import Trainer
-            epoch = {'batches': (len(rows) + BATCH - 1) // BATCH,
-                     'how': 'wall clock of Trainer.train_epoch (negative sampling, shuffling, batching, H2D, steps, loss reads), after one warm-up epoch'}
-            for key, loader in (('device_loader', DeviceLoader(DeviceTrnData(trn, dev, 2023), BATCH)), ('host_dataloader', dh.train_dataloader)):
-                tr = Trainer(types.SimpleNamespace(train_dataloader=loader))
-                tr.optimizer = opt
-                best = None
-                for rep in range(3 if key == 'device_loader' else 2):
+            try:
+                import types
+                from sslrec_b200.data_handler import DeviceLoader, DeviceTrnData
+                from sslrec_b200.trainer import Trainer
+                epoch = {'batches': (len(rows) + BATCH - 1) // BATCH,
+                         'how': 'wall clock of Trainer.train_epoch (negative sampling, shuffling, batching, H2D, steps, loss reads), after one warm-up epoch'}
+                import torch.utils.data as tdata
+                epoch['loaders'] = ('device_loader = train.device_loader: true (pairs, negative sampling, shuffle and batching on the device); host_dataloader = the data '
+                                    'handler\'s default (HostBatchLoader: the reference\'s DataLoader(shuffle=True) batch for batch, gathered by array indexing); '
+                                    'torch_dataloader = torch.utils.data.DataLoader itself over the same dataset (the reference\'s data path)')
+                for key, loader in (('device_loader', DeviceLoader(DeviceTrnData(trn, dev, 2023), BATCH)), ('host_dataloader', dh.train_dataloader),
+                                    ('torch_dataloader', tdata.DataLoader(dh.train_dataloader.dataset, batch_size=BATCH, shuffle=True, num_workers=0))):
+                    tr = Trainer(types.SimpleNamespace(train_dataloader=loader))
+                    tr.optimizer = opt
+                    best = None
+                    for rep in range(2 if key == 'torch_dataloader' else 3):
+                        torch.cuda.synchronize()
+                        t0 = time.perf_counter()
+                        tr.train_epoch(model, rep)
+                        torch.cuda.synchronize()
+                        dt = time.perf_counter() - t0
+                        best = dt if (best is None or rep == 1) else min(best, dt)      # rep 0 is the warm-up
+                    epoch[key + '_steps_per_sec'] = len(loader) / best
+                    epoch[key + '_epoch_s'] = best
+            except Exception as e:      # noqa: BLE001 -- an extra record must never cost the bench line
+                epoch = {'error': repr(e)[:400]}
+
+        # ---- one all-rank evaluation pass through Trainer.evaluate (full_predict + _mask_predict from the device CSR, native top-40, metrics on the
+        # host; trainer.py:139-150 + metrics.py:82-127) over every user, one synthetic held-out item each ----
+        evalrec = None
+        if world == 1 and args.workload == 'simgcl-amazon':
+            try:
+                import types
+                import torch.utils.data as tdata
+                from sslrec_b200.data_handler import AllRankTstData
+                from sslrec_b200.trainer import Trainer
+                rs = np.random.RandomState(7)
+                val = sp.coo_matrix((np.ones(n_user, dtype=np.float32), (np.arange(n_user), rs.randint(0, n_item, n_user))), shape=(n_user, n_item))
+                ld = tdata.DataLoader(AllRankTstData(val, trn, dense_mask=False), batch_size=cfg['test']['batch_size'], shuffle=False, num_workers=0)
+                tr = Trainer(types.SimpleNamespace())
+                secs = []
+                for rep in range(2):                                     # rep 0 warms up (first propagation in eval mode, truth CSR)
                     torch.cuda.synchronize()
                     t0 = time.perf_counter()
-                    tr.train_epoch(model, rep)
+                    res = tr.evaluate(model, loader=ld)
                     torch.cuda.synchronize()
-                    dt = time.perf_counter() - t0
-                    best = dt if (best is None or rep == 1) else min(best, dt)      # rep 0 is the warm-up
-                epoch[key + '_steps_per_sec'] = len(loader) / best
-                epoch[key + '_epoch_s'] = best
+                    secs.append(time.perf_counter() - t0)
+                evalrec = {'users': n_user, 'batches': len(ld), 'eval_batch': cfg['test']['batch_size'], 'k': cfg['test']['k'], 'seconds': secs[-1],
+                           'users_per_sec': n_user / secs[-1], 'recall': [float(v) for v in res['recall']],
+                           'how': 'wall clock of Trainer.evaluate over all users: ssl_predict_mask (training positives masked from the device CSR) + ssl_topk '
+                                  'per 1024-user batch, D2H of the top-40 indices, vectorised recall / ndcg on the host'}
+                model.train()
+            except Exception as e:      # noqa: BLE001 -- an extra record must never cost the bench line
+                evalrec = {'error': repr(e)[:400]}
 
         # ---- the same step captured in ONE CUDA graph (sslrec_b200.graphed.GraphedStep; `train.cuda_graph: true` in the trainer), measured in
         # its own process: a capture that fails must not be able to touch this process's CUDA / RNG state ----
@@ -659,7 +695,7 @@ def run_ours(args):
                 'strict_sync_how': 'the reference trainer\'s own loop: blocking loss.item() after cal_loss and float(v) per loss term (trainer.py:66,72)'},
             'e2e_strict_sync': {'value': units * 1e3 / ms_e2e_strict, 'unit': 'steps/s', 'ms_per_step': ms_e2e_strict,
                                 'how': 'the reference trainer\'s blocking reads: loss.item() after cal_loss and float(v) per loss term (trainer.py:66,72)'},
-            'e2e_epoch': epoch,
+            'e2e_epoch': epoch, 'e2e_eval': evalrec,
             'gpu_launches': launches, 'gpu_launches_per_step': launches / K,
             'embeddings_propagated_per_sec': emb_per_step * value,
             'roofline': roofline, 'roofline_infonce': roofline_nce, 'cpu_baseline': cpu, 'row_shard': None, 'cuda_graph': graphed, 'eval_kernels': eval_kernels,

@@ -241,3 +241,105 @@ def test_vectorised_evaluation_metrics_match_the_per_user_loop_and_do_not_depend
         assert np.abs(a[m] - want[m]).max() < 1e-13, m
         assert np.array_equal(a[m], b[m]), m
     assert want['recall'][0] > 0 and want['mrr'][2] > 0
+
+
+def test_trainer_evaluate_end_to_end_with_a_stub_model(monkeypatch):
+    """Trainer.evaluate's plumbing on the CPU (the kernels behind full_predict / topk are covered by the GPU tests): loader batches ->
+    full_predict -> top-k -> vectorised metrics, for the dense-mask loader of the reference and the lean (device-CSR) loader, against
+    the loop form of metrics.py:82-127 on the same scores."""
+    import scipy.sparse as sp
+    import torch.utils.data as tdata
+    from sslrec_b200 import trainer as T
+    from sslrec_b200.config import default_config, load_config
+    from sslrec_b200.data_handler import AllRankTstData
+    load_config(base=default_config('lightgcn'), device='cpu')
+    rs = np.random.RandomState(4)
+    U, I = 333, 150
+    trn = sp.coo_matrix((np.ones(900), (rs.randint(0, U, 900), rs.randint(0, I, 900))), shape=(U, I))
+    val = sp.coo_matrix((np.ones(500), (rs.randint(0, U - 20, 500), rs.randint(0, I, 500))), shape=(U, I))      # the last users have no held-out item
+    scores = torch.from_numpy(rs.rand(U, I).astype(np.float32))
+    trn_mask = torch.from_numpy((trn.tocsr().toarray() != 0))
+
+    class Model(torch.nn.Module):
+        def full_predict(self, batch_data):
+            users, mask = batch_data
+            s = scores[users]
+            m = trn_mask[users] if isinstance(mask, str) else mask.bool()
+            return torch.where(m, torch.full_like(s, -1e8), s)
+    monkeypatch.setattr(T, 'topk', lambda preds, k: torch.topk(preds, k).indices)
+    tr = T.Trainer(types.SimpleNamespace())
+    res = {}
+    for dense in (True, False):
+        ds = AllRankTstData(val, trn, dense_mask=dense)
+        res[dense] = tr.evaluate(Model(), loader=tdata.DataLoader(ds, batch_size=64, shuffle=False))
+    for m in ('recall', 'ndcg'):
+        assert np.array_equal(res[True][m], res[False][m])
+    ds = AllRankTstData(val, trn)
+    ks, n = [10, 20, 40], len(ds.test_users)
+    want = {'recall': np.zeros(3), 'ndcg': np.zeros(3)}
+    for u in ds.test_users:
+        s = torch.where(trn_mask[u], torch.tensor(-1e8), scores[u])
+        top = torch.topk(s, 40).indices.numpy()
+        truth = ds.user_pos_lists[u]
+        hit = np.isin(top, truth).astype(np.float64)
+        for ki, k in enumerate(ks):
+            want['recall'][ki] += hit[:k].sum() / len(truth) / n
+            want['ndcg'][ki] += (hit[:k] / np.log2(np.arange(2, k + 2))).sum() / (1.0 / np.log2(np.arange(2, min(k, len(truth)) + 2))).sum() / n
+    for m in want:
+        assert np.abs(res[True][m] - want[m]).max() < 1e-12 and want[m][2] > 0
+
+
+def test_host_batch_loader_is_the_torch_dataloader_batch_for_batch():
+    """data_handler.HostBatchLoader against torch.utils.data.DataLoader(trn_data, batch_size, shuffle=True) (data_handler_general_cf.py:95)
+    under the same global seed: identical batches (values and dtypes) over several epochs, identical epoch flags of NCL's dataset, and
+    the same state of torch's global generator afterwards."""
+    import scipy.sparse as sp
+    import torch.utils.data as tdata
+    from sslrec_b200.config import default_config, load_config
+    from sslrec_b200.data_handler import HostBatchLoader, PairwiseTrnData, PairwiseWEpochFlagTrnData
+    load_config(base=default_config('ncl', epoch_period=2), device='cpu')
+    rs = np.random.RandomState(0)
+    U, I = 300, 200
+    key = np.unique(rs.randint(0, U, 5000).astype(np.int64) * I + rs.randint(0, I, 5000))
+    m = sp.coo_matrix((np.ones(len(key)), (key // I, key % I)), shape=(U, I))
+    for cls in (PairwiseTrnData, PairwiseWEpochFlagTrnData):
+        runs = []
+        for make in (lambda d: tdata.DataLoader(d, batch_size=256, shuffle=True, num_workers=0), lambda d: HostBatchLoader(d, 256)):
+            d = cls(m)
+            loader = make(d)
+            torch.manual_seed(5)
+            np.random.seed(1)
+            epochs = []
+            for _ in range(5):
+                d.sample_negs()
+                epochs.append([[t.clone() for t in batch] for batch in loader])
+            runs.append((len(loader), epochs, torch.get_rng_state()))
+        (la, ea, ra), (lb, eb, rb) = runs
+        assert la == lb and torch.equal(ra, rb)
+        for x, y in zip(ea, eb):
+            assert len(x) == len(y)
+            for bx, by in zip(x, y):
+                assert isinstance(by, list) and len(bx) == len(by)
+                assert all(t.dtype == u.dtype and torch.equal(t, u) for t, u in zip(bx, by))
+        if cls is PairwiseWEpochFlagTrnData:
+            assert [int(sum(b[3].sum() for b in e)) for e in eb] == [1, 1, 0, 1, 0]
+
+
+def test_data_handler_default_train_loader():
+    import scipy.sparse as sp
+    import torch.utils.data as tdata
+    from sslrec_b200.config import default_config, load_config
+    from sslrec_b200.data_handler import DataHandlerGeneralCF, HostBatchLoader
+    rs = np.random.RandomState(1)
+    m = sp.coo_matrix((np.ones(400), (rs.randint(0, 50, 400), rs.randint(0, 40, 400))), shape=(50, 40))
+    cfg = default_config('lightgcn')
+    cfg['train']['batch_size'] = 64
+    load_config(base=cfg, device='cpu')
+    dh = DataHandlerGeneralCF(m, m, m)
+    dh.load_data()
+    assert isinstance(dh.train_dataloader, HostBatchLoader) and len(dh.train_dataloader) == (len(dh.train_dataloader.dataset) + 63) // 64
+    cfg['train']['torch_dataloader'] = True
+    load_config(base=cfg, device='cpu')
+    dh = DataHandlerGeneralCF(m, m, m)
+    dh.load_data()
+    assert isinstance(dh.train_dataloader, tdata.DataLoader)
