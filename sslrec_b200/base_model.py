@@ -136,7 +136,8 @@ class BaseModel(nn.Module):
         """E_u[users] E_i^T with the training positives masked to -1e8 (lightgcn.py:61-65, base_model.py:35-36) in
         one kernel; no [Bt, I] temporaries besides the result.  ``train_mask``: the reference's dense [Bt, I] 0/1
         tensor, or None = no masking, or the string 'train' = mask the user's training items from the device CSR."""
-        pck_users, train_mask = batch_data
+        # [users] alone (a lean AllRankTstData batch driven by the reference's Metric.eval, metrics.py:94-101) = mask from the device CSR
+        pck_users, train_mask = (batch_data[0], 'train') if len(batch_data) == 1 else batch_data
         pck_users = pck_users.long().contiguous()
         n_b = pck_users.shape[0]
         preds = torch.empty(n_b, self.item_num, device=user_embeds.device, dtype=torch.float32)

@@ -293,7 +293,9 @@ class DataHandlerGeneralCF:
                 self.train_dataloader = data.DataLoader(trn_data, batch_size=configs['train']['batch_size'], shuffle=True, num_workers=0)
             else:
                 self.train_dataloader = HostBatchLoader(trn_data, configs['train']['batch_size'])
-        dense = configs['test'].get('dense_mask', True)      # optional key: False = mask on device from the training CSR
+        # optional key test.dense_mask: true = the reference's dense float64 [I] train-mask row per test user, built on the host and shipped per
+        # batch (datasets_general_cf.py:64-68; 686 MB per 1024-user batch at the amazon shape); default: the model masks from its device CSR
+        dense = configs['test'].get('dense_mask', False)
         if val_mat is not None:
             self.valid_dataloader = data.DataLoader(AllRankTstData(val_mat, trn_mat, dense), batch_size=configs['test']['batch_size'], shuffle=False, num_workers=0)
         if tst_mat is not None:

@@ -143,6 +143,7 @@ def test_trainer_epochs_and_evaluate(name):
         cfg['train']['device_loader'] = True                     # pairs, negative sampling and batching on the device
     cfg['optimizer']['lr'] = 5e-3
     cfg['test']['batch_size'] = 256
+    cfg['test']['dense_mask'] = True                             # the reference's dense train-mask rows; the lean loader is compared below
     load_config(base=cfg, device='cuda')
     init_seed()
     U, I = case['n_user'], case['n_item']
