@@ -222,7 +222,7 @@ class Trainer(object):
 
 def truth_csr(ds):
     """The held-out positives of an AllRankTstData (``user_pos_lists``, datasets_general_cf.py:52-58) as one flat CSR (ptr int64
-    [n_user + 1], items int64), built once per dataset."""
+    [n_user + 1], items int64 ascending inside a user's list), built once per dataset."""
     cached = getattr(ds, '_truth_csr', None)
     if cached is None:
         import itertools
@@ -231,6 +231,8 @@ def truth_csr(ds):
         ptr = np.zeros(len(lists) + 1, dtype=np.int64)
         np.cumsum(lens, out=ptr[1:])
         flat = np.fromiter(itertools.chain.from_iterable(lists), dtype=np.int64, count=int(ptr[-1]))
+        owner = np.repeat(np.arange(len(lists), dtype=np.int64), lens)
+        flat = flat[np.lexsort((flat, owner))]                # ascending inside every user's list: a batch's (row, item) keys come out sorted
         cached = ds._truth_csr = (ptr, flat)
     return cached
 
@@ -252,8 +254,13 @@ def batch_metric_rows(top, users, ptr, flat, ks, metrics):
     within = np.arange(total, dtype=np.int64) - np.repeat(first, lens)
     truth_items = flat[np.repeat(ptr[users], lens) + within]
     base = int(max(top.max(initial=0), truth_items.max(initial=0))) + 1
-    truth_keys = np.repeat(np.arange(n, dtype=np.int64), lens) * base + truth_items
-    hit = np.isin(np.arange(n, dtype=np.int64)[:, None] * base + top, truth_keys).astype(np.float64)
+    truth_keys = np.repeat(np.arange(n, dtype=np.int64), lens) * base + truth_items      # ascending (rows ascending, items ascending per row)
+    top_keys = np.arange(n, dtype=np.int64)[:, None] * base + top
+    if total:
+        pos = np.minimum(np.searchsorted(truth_keys, top_keys), total - 1)
+        hit = (truth_keys[pos] == top_keys).astype(np.float64)
+    else:
+        hit = np.zeros(top.shape)
     disc = 1.0 / np.log2(np.arange(2, kmax + 2))              # 1 / log2(rank + 1)
     ideal = np.cumsum(disc)                                   # idcg of a user with j + 1 positives at a cut-off >= j + 1
     denom = np.maximum(lens, 1)
