@@ -27,12 +27,27 @@ def init_seed():
             torch.cuda.manual_seed_all(seed)
 
 
+def _summary_writer():
+    """The optional TensorBoard writer of trainer.py:20-23 (``train.tensorboard: true`` -> SummaryWriter('runs')); None otherwise."""
+    if not configs.get('train', {}).get('tensorboard', False):
+        return None
+    from torch.utils.tensorboard import SummaryWriter
+    return SummaryWriter(log_dir='runs')
+
+
 class Trainer(object):
     def __init__(self, data_handler, logger=None, grad_sync=None):
         self.data_handler = data_handler
         self.logger = logger
         self.grad_sync = grad_sync     # parallel.BatchShard: data-parallel ranks average gradients before the step
         self._graphed = None           # graphed.GraphedStep when train.cuda_graph is set
+        self._writer = None            # created on first use: the scalars 'Loss/train' and 'HR/test' of trainer.py:78,144
+
+    def _scalar(self, tag, value, step):
+        if self._writer is None and configs.get('train', {}).get('tensorboard', False):
+            self._writer = _summary_writer()
+        if self._writer is not None:
+            self._writer.add_scalar(tag, value, step)
 
     def create_optimizer(self, model):
         optim_config = configs['optimizer']
@@ -76,6 +91,8 @@ class Trainer(object):
             ep_loss += done[0]
             for loss_name, val in done[1].items():
                 loss_log_dict[loss_name] = loss_log_dict.get(loss_name, 0.0) + val / len(train_dataloader)
+        steps = len(train_dataloader.dataset) // configs['train']['batch_size']                   # trainer.py:60,78
+        self._scalar('Loss/train', ep_loss / max(steps, 1), epoch_idx)
         if self.logger is not None:
             self.logger.log_loss(epoch_idx, loss_log_dict, save_to_log=configs['train'].get('log_loss', True))
         return ep_loss, loss_log_dict
@@ -150,7 +167,11 @@ class Trainer(object):
         """trainer.py:152-160: metrics on the test split."""
         if not hasattr(self.data_handler, 'test_dataloader'):
             raise NotImplementedError('data handler has no test_dataloader')
-        return self.evaluate(model, loader=self.data_handler.test_dataloader, data_type='Test set')
+        self._in_test = True                 # the reference's test() writes no TensorBoard scalar (trainer.py:152-160)
+        try:
+            return self.evaluate(model, loader=self.data_handler.test_dataloader, data_type='Test set')
+        finally:
+            self._in_test = False
 
     def save_model(self, model):
         """trainer.py:162-186: ./checkpoint/{model}/{model}-{data}-{timestamp}.pth (tune runs: ./checkpoint/{model}/tune/
@@ -215,6 +236,8 @@ class Trainer(object):
         assert seen == n_users, 'evaluation did not cover every test user (metrics.py:113)'
         # one sum over all users in loader order: the result does not depend on how the users were batched
         result = {m: (np.concatenate(per_user[m]).sum(0) / n_users if per_user[m] else np.zeros(len(ks))) for m in metrics}
+        if not getattr(self, '_in_test', False):
+            self._scalar('HR/test', float(result[metrics[0]][0]), epoch_idx)                       # trainer.py:144,148 (evaluate only, not test)
         if self.logger is not None:
             self.logger.log_eval(result, ks, data_type=data_type or 'Validation set', epoch_idx=epoch_idx)
         return result

@@ -343,3 +343,26 @@ def test_data_handler_default_train_loader():
     dh = DataHandlerGeneralCF(m, m, m)
     dh.load_data()
     assert isinstance(dh.train_dataloader, tdata.DataLoader)
+
+
+def test_trainer_tensorboard_scalars(tmp_path, monkeypatch):
+    """train.tensorboard: true -> the scalars of trainer.py:78,144 ('Loss/train' per epoch, 'HR/test' per evaluate, none for test)."""
+    from sslrec_b200 import trainer as T
+    from sslrec_b200.config import default_config, load_config
+    cfg = default_config('lightgcn')
+    cfg['train']['tensorboard'] = True
+    load_config(base=cfg, device='cpu')
+    calls = []
+
+    class Writer:
+        def add_scalar(self, tag, value, step):
+            calls.append((tag, round(float(value), 6), step))
+    monkeypatch.setattr(T, '_summary_writer', lambda: Writer())
+    tr = T.Trainer(types.SimpleNamespace())
+    tr._scalar('Loss/train', 0.5, 3)
+    assert calls == [('Loss/train', 0.5, 3)]
+    cfg['train']['tensorboard'] = False
+    load_config(base=cfg, device='cpu')
+    tr2 = T.Trainer(types.SimpleNamespace())
+    tr2._scalar('Loss/train', 0.5, 3)
+    assert len(calls) == 1 and tr2._writer is None
