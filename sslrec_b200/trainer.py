@@ -220,7 +220,7 @@ class Trainer(object):
         n_users = len(ds.test_users)
         ptr, flat = truth_csr(ds)
         seen = 0
-        for tem in loader:
+        for tem in _eval_batches(loader):
             if not isinstance(tem, (list, tuple)):
                 tem = [tem]
             users = tem[0].numpy().astype(np.int64)
@@ -241,6 +241,19 @@ class Trainer(object):
         if self.logger is not None:
             self.logger.log_eval(result, ks, data_type=data_type or 'Validation set', epoch_idx=epoch_idx)
         return result
+
+
+def _eval_batches(loader):
+    """The loader's batches.  A sequential torch DataLoader over a lean AllRankTstData (user ids only: ``dense_mask=False``) is served as
+    slices of ``test_users`` -- the same batches without 76 k ``__getitem__`` calls and collates per amazon-sized evaluation."""
+    from .data_handler import AllRankTstData
+    import torch.utils.data as tdata
+    ds = getattr(loader, 'dataset', None)
+    if (isinstance(loader, tdata.DataLoader) and isinstance(ds, AllRankTstData) and not ds.dense_mask and loader.batch_size
+            and isinstance(loader.sampler, tdata.SequentialSampler) and not loader.drop_last):
+        users = torch.from_numpy(np.ascontiguousarray(ds.test_users))
+        return (users[lo:lo + loader.batch_size] for lo in range(0, users.numel(), loader.batch_size))
+    return iter(loader)
 
 
 def truth_csr(ds):

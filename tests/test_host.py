@@ -366,3 +366,22 @@ def test_trainer_tensorboard_scalars(tmp_path, monkeypatch):
     tr2 = T.Trainer(types.SimpleNamespace())
     tr2._scalar('Loss/train', 0.5, 3)
     assert len(calls) == 1 and tr2._writer is None
+
+
+def test_lean_evaluation_batches_equal_the_dataloader_batches():
+    import scipy.sparse as sp
+    import torch.utils.data as tdata
+    from sslrec_b200.config import default_config, load_config
+    from sslrec_b200.data_handler import AllRankTstData
+    from sslrec_b200.trainer import _eval_batches
+    load_config(base=default_config('lightgcn'), device='cpu')
+    rs = np.random.RandomState(1)
+    U, I = 500, 80
+    trn = sp.coo_matrix((np.ones(900), (rs.randint(0, U, 900), rs.randint(0, I, 900))), shape=(U, I))
+    val = sp.coo_matrix((np.ones(300), (rs.randint(0, U, 300), rs.randint(0, I, 300))), shape=(U, I))
+    lean = tdata.DataLoader(AllRankTstData(val, trn, dense_mask=False), batch_size=64, shuffle=False, num_workers=0)
+    a, b = [x.clone() for x in lean], list(_eval_batches(lean))
+    assert len(a) == len(b) and all(x.dtype == y.dtype and torch.equal(x, y) for x, y in zip(a, b))
+    dense = tdata.DataLoader(AllRankTstData(val, trn, dense_mask=True), batch_size=64, shuffle=False)
+    first = next(iter(_eval_batches(dense)))
+    assert isinstance(first, list) and len(first) == 2 and first[1].shape == (64, I)          # the reference's [users, mask] batches untouched
