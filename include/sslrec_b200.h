@@ -53,6 +53,8 @@ SSL_API int64_t ssl_launch_count(void);
 /* process-wide switches for tests and A/B profiling (value 0 / 1):
  *   "prop_view_major"  propagation with grid.y = view and one accumulator per thread: DRAM traffic at 1.03x compulsory instead of
  *                      1.3x, but 25-40 % slower on B200 (profiles/r02_prop_variants.md); default 0
+ *   "kmeans_rows_per_round"  1 selects kmeans_assign_kernel<1> (one row per warp and round, the round-1 form); default 4 rows per round --
+ *                      same arithmetic per (row, centroid), same summation order: bit-identical results (csrc/kmeans_assign.cuh)
  *   "predict_tiled"    ssl_predict_mask as a register-tiled product (128 x 128 score tiles, csrc/predict_tile.cuh); 0 selects the
  *                      round-1 warp-per-item kernel (4 % of the FFMA rate, profiles/r02_ncu_kernels.md), kept as the cross-check; default 1 */
 SSL_API int ssl_set_option(const char *name, int64_t value);

@@ -19,6 +19,7 @@ void set_error(const char *fmt, ...) {
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 int g_predict_tiled = 1;
+int g_kmeans_rows_per_round = 4;
 }  // namespace ssl
 
 extern "C" int ssl_version(void) { return 100; }

@@ -1,93 +1,9 @@
 // a17  KMeansClustering (models/aug_utils.py:142-157): Lloyd iterations, deterministic.
 // a21  PairwiseTrnData.sample_negs (data_utils/datasets_general_cf.py:13-26): uniform rejection sampling.
 #include "common.cuh"
+#include "kmeans_assign.cuh"
 
 namespace {
-
-// ---------------------------------------------------------------------------------------------
-// One Lloyd assignment pass (aug_utils.py:150-155).  Rows are split STATICALLY: CTA b owns a
-// contiguous chunk, warp w of it a contiguous sub-chunk it walks in order, adding each row into its
-// own [K, d] slab in shared memory.  The slabs are summed in warp order and written as one partial
-// per CTA; kmeans_update_kernel sums the partials in CTA order.  No floating-point atomics: the
-// centroids are a pure function of the inputs, whatever the scheduling.
-// Distances: lane l evaluates centroid k = 32 r + l against the row staged in shared memory,
-// sum_j (x_j - c_kj)^2 in index order (the reference's (x - c).square().sum(-1)); centroid rows are
-// padded to d + 1 floats so the 32 lanes hit 32 banks.  argmin ties -> lowest centroid id.
-// ---------------------------------------------------------------------------------------------
-__global__ void kmeans_assign_kernel(const float *__restrict__ x, int64_t stride, int64_t n, int dim, int K,
-                                     const float *__restrict__ cents, int64_t *__restrict__ assign,
-                                     float *__restrict__ part_sum, float *__restrict__ part_cnt,
-                                     int *__restrict__ changed, int64_t rows_per_cta, int64_t rows_per_warp) {
-    extern __shared__ float smem[];
-    const int W = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int cpad = dim + 1;
-    float *cs = smem;                              // [K, dim + 1]
-    float *xs = cs + (size_t)K * cpad;             // [W, dim]
-    float *slab = xs + (size_t)W * dim;            // [W, K, dim]
-    float *cnt = slab + (size_t)W * K * dim;       // [W, K]
-    for (int e = threadIdx.x; e < K * dim; e += blockDim.x) cs[(e / dim) * cpad + (e % dim)] = cents[e];
-    for (int e = threadIdx.x; e < W * K * dim; e += blockDim.x) slab[e] = 0.f;
-    for (int e = threadIdx.x; e < W * K; e += blockDim.x) cnt[e] = 0.f;
-    __syncthreads();
-
-    float *myx = xs + (size_t)warp * dim;
-    float *myslab = slab + (size_t)warp * K * dim;
-    const int64_t cta0 = (int64_t)blockIdx.x * rows_per_cta;
-    const int64_t r0 = cta0 + (int64_t)warp * rows_per_warp;
-    const int64_t cta_end = cta0 + rows_per_cta < n ? cta0 + rows_per_cta : n;
-    const int64_t r1 = r0 + rows_per_warp < cta_end ? r0 + rows_per_warp : cta_end;
-    int n_changed = 0;
-    for (int64_t r = r0; r < r1; ++r) {
-        const float *xr = x + r * stride;
-        for (int j = lane; j < dim; j += 32) myx[j] = __ldg(xr + j);
-        __syncwarp();
-        float best = INFINITY;
-        int best_k = 0x7fffffff;
-        for (int k = lane; k < K; k += 32) {
-            const float *c = cs + (size_t)k * cpad;
-            float d2 = 0.f;
-            for (int j = 0; j < dim; ++j) {
-                const float t = myx[j] - c[j];
-                d2 = fmaf(t, t, d2);
-            }
-            if (d2 < best) {                       // k ascends per lane: strict < keeps the lowest id
-                best = d2;
-                best_k = k;
-            }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-            const int ok = __shfl_xor_sync(0xffffffffu, best_k, o);
-            if (ob < best || (ob == best && ok < best_k)) {
-                best = ob;
-                best_k = ok;
-            }
-        }
-        if (best_k >= K) best_k = 0;               // all distances NaN: torch.min returns index 0 as well
-        float *dst = myslab + (size_t)best_k * dim;
-        for (int j = lane; j < dim; j += 32) dst[j] += myx[j];
-        if (lane == 0) {
-            cnt[warp * K + best_k] += 1.f;
-            if (assign[r] != (int64_t)best_k) ++n_changed;
-            assign[r] = best_k;
-        }
-        __syncwarp();
-    }
-    if (lane == 0 && n_changed) atomicAdd(changed, n_changed);
-    __syncthreads();
-    float *ps = part_sum + (size_t)blockIdx.x * K * dim;
-    for (int e = threadIdx.x; e < K * dim; e += blockDim.x) {
-        float s = 0.f;
-        for (int w = 0; w < W; ++w) s += slab[(size_t)w * K * dim + e];
-        ps[e] = s;
-    }
-    for (int e = threadIdx.x; e < K; e += blockDim.x) {
-        float s = 0.f;
-        for (int w = 0; w < W; ++w) s += cnt[w * K + e];
-        part_cnt[(size_t)blockIdx.x * K + e] = s;
-    }
-}
 
 // centroids = newCents / (clustNums + 1e-6)   (aug_utils.py:156)
 __global__ void kmeans_update_kernel(const float *__restrict__ part_sum, const float *__restrict__ part_cnt, int n_cta, int K,
@@ -152,7 +68,8 @@ __global__ void sample_negs_kernel(const int64_t *__restrict__ users, int64_t n_
 extern "C" int ssl_kmeans_workspace(int64_t n, int32_t dim, int32_t k, int32_t *n_cta, int32_t *n_warps) {
     SSL_CHECK_ARG(n > 0 && dim > 0 && k > 0 && n_cta && n_warps, "ssl_kmeans_workspace: bad arguments");
     int W = 8;
-    auto smem = [&](int w) { return sizeof(float) * ((size_t)k * (dim + 1) + (size_t)w * dim + (size_t)w * k * dim + (size_t)w * k); };
+    // sized for the widest instantiation, whichever runs: the row partition (and with it every partial sum) does not depend on the option
+    auto smem = [&](int w) { return sizeof(float) * ssl_kmeans::smem_floats(k, dim, w, ssl_kmeans::kMaxRowsPerRound); };
     while (W > 1 && smem(W) > 200 * 1024) W >>= 1;
     SSL_CHECK_ARG(smem(W) <= 200 * 1024, "ssl_kmeans: cluster_num * dim = %lld does not fit shared memory", (long long)k * dim);
     int64_t ctas = (n + (int64_t)W * 8 - 1) / ((int64_t)W * 8);      // at least ~8 rows per warp
@@ -170,12 +87,20 @@ extern "C" int ssl_kmeans_iter(const float *x, int64_t stride, int64_t n, int32_
     if (rc != SSL_OK) return rc;
     SSL_CHECK_ARG(stride >= dim, "ssl_kmeans_iter: stride < dim");
     cudaStream_t s = (cudaStream_t)stream;
-    const size_t smem = sizeof(float) * ((size_t)k * (dim + 1) + (size_t)W * dim + (size_t)W * k * dim + (size_t)W * k);
-    SSL_CUDA(cudaFuncSetAttribute(kmeans_assign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t rows_per_cta = (n + n_cta - 1) / n_cta;
     const int64_t rows_per_warp = (rows_per_cta + W - 1) / W;
-    kmeans_assign_kernel<<<n_cta, W * 32, smem, s>>>(x, stride, n, dim, k, centroids, assign, part_sum, part_cnt, changed,
-                                                     rows_per_cta, rows_per_warp);
+    if (ssl::g_kmeans_rows_per_round > 1) {      // default: 4 rows per warp and round (4 independent distance chains per lane), results bit-identical
+        constexpr int R = ssl_kmeans::kMaxRowsPerRound;
+        const size_t smem = sizeof(float) * ssl_kmeans::smem_floats(k, dim, W, R);
+        SSL_CUDA(cudaFuncSetAttribute(ssl_kmeans::kmeans_assign_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ssl_kmeans::kmeans_assign_kernel<R><<<n_cta, W * 32, smem, s>>>(x, stride, n, dim, k, centroids, assign, part_sum, part_cnt, changed,
+                                                                       rows_per_cta, rows_per_warp);
+    } else {
+        const size_t smem = sizeof(float) * ssl_kmeans::smem_floats(k, dim, W, 1);
+        SSL_CUDA(cudaFuncSetAttribute(ssl_kmeans::kmeans_assign_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ssl_kmeans::kmeans_assign_kernel<1><<<n_cta, W * 32, smem, s>>>(x, stride, n, dim, k, centroids, assign, part_sum, part_cnt, changed,
+                                                                       rows_per_cta, rows_per_warp);
+    }
     SSL_LAUNCH_CHECK("kmeans_assign_kernel");
     kmeans_update_kernel<<<(k * dim + 255) / 256, 256, 0, s>>>(part_sum, part_cnt, n_cta, k, dim, centroids, counts);
     SSL_LAUNCH_CHECK("kmeans_update_kernel");

@@ -10,6 +10,7 @@ namespace ssl {
 
 void set_error(const char *fmt, ...);
 void count_launch(int n = 1);
+extern int g_kmeans_rows_per_round;   // ssl_set_option("kmeans_rows_per_round", v): 4 (default) or 1 -- kmeans_assign_kernel<R>, bit-identical results
 extern int g_predict_tiled;   // ssl_set_option("predict_tiled", v): 1 (default) = predict_tile_kernel, 0 = the warp-per-item kernel
 
 #define SSL_CHECK_ARG(cond, ...)                \

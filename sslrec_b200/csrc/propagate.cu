@@ -392,6 +392,10 @@ extern "C" int ssl_set_option(const char *name, int64_t value) {
         g_view_major = value == 0;
         return SSL_OK;
     }
+    if (n == "kmeans_rows_per_round") {     // 1: kmeans_assign_kernel<1> (one row per warp and round); anything else: the default <4>
+        ssl::g_kmeans_rows_per_round = value == 1 ? 1 : 4;
+        return SSL_OK;
+    }
     if (n == "predict_tiled") {             // 0: the warp-per-item score kernel instead of the tiled one (ssl_predict_mask)
         ssl::g_predict_tiled = value != 0;
         return SSL_OK;

@@ -7,6 +7,7 @@
 #include <math.h>
 #include <pthread.h>
 #include <stdint.h>
+#include <string.h>
 
 #include <functional>
 #include <vector>
@@ -20,13 +21,38 @@ static thread_local dim3 threadIdx, blockIdx;
 static dim3 blockDim, gridDim;
 static pthread_barrier_t emu_barrier;
 
+// warp-level primitives: the 32 lanes of a warp are 32 pthreads; a convergent warp operation is two waits on the warp's barrier
+// around an exchange buffer (the kernels this header serves call them from warp-uniform control flow only)
+constexpr int EMU_MAX_WARPS = 32;
+static pthread_barrier_t emu_warp_barrier[EMU_MAX_WARPS];
+static uint32_t emu_xchg[EMU_MAX_WARPS][32];
+static float *emu_dyn_smem_ptr = nullptr;      // "extern __shared__": one buffer per launch, shared by the block's threads
+static inline float *emu_dyn_smem_float() { return emu_dyn_smem_ptr; }
+static inline int emu_linear_tid() { return (int)(threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z)); }
+
 #define __global__
 #define __shared__ static
 #define __launch_bounds__(...)
 #define __device__
 #define __forceinline__ inline
 
+#define __host__
 static inline void __syncthreads() { pthread_barrier_wait(&emu_barrier); }
+static inline void __syncwarp(unsigned = 0xffffffffu) { pthread_barrier_wait(&emu_warp_barrier[emu_linear_tid() >> 5]); }
+template <class T>
+static inline T __shfl_xor_sync(unsigned, T v, int lane_mask) {
+    static_assert(sizeof(T) == 4, "32-bit shuffles only");
+    const int w = emu_linear_tid() >> 5, l = emu_linear_tid() & 31;
+    memcpy(&emu_xchg[w][l], &v, 4);
+    pthread_barrier_wait(&emu_warp_barrier[w]);
+    T r;
+    memcpy(&r, &emu_xchg[w][l ^ lane_mask], 4);
+    pthread_barrier_wait(&emu_warp_barrier[w]);
+    return r;
+}
+template <class T>
+static inline T __ldg(const T *p) { return *p; }
+static inline int atomicAdd(int *p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 
 struct EmuThread {
     dim3 t, b;
@@ -47,6 +73,9 @@ static inline void emu_launch(dim3 grid, dim3 block, const std::function<void()>
     blockDim = block;
     const unsigned nt = block.x * block.y * block.z;
     pthread_barrier_init(&emu_barrier, nullptr, nt);
+    const unsigned n_warps = (nt + 31) / 32;
+    for (unsigned w = 0; w < n_warps && w < (unsigned)EMU_MAX_WARPS; ++w)
+        pthread_barrier_init(&emu_warp_barrier[w], nullptr, (w + 1) * 32 <= nt ? 32 : nt - w * 32);
     for (unsigned bz = 0; bz < grid.z; ++bz)
         for (unsigned by = 0; by < grid.y; ++by)
             for (unsigned bx = 0; bx < grid.x; ++bx) {
@@ -62,4 +91,5 @@ static inline void emu_launch(dim3 grid, dim3 block, const std::function<void()>
                 for (unsigned i = 0; i < nt; ++i) pthread_join(th[i], nullptr);
             }
     pthread_barrier_destroy(&emu_barrier);
+    for (unsigned w = 0; w < n_warps && w < (unsigned)EMU_MAX_WARPS; ++w) pthread_barrier_destroy(&emu_warp_barrier[w]);
 }

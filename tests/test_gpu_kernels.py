@@ -397,6 +397,27 @@ def test_negative_sampler_bit_exact_and_valid(n_user, n_item, n_edge):
     assert len(np.unique(both[:, 0] * n_item + both[:, 1])) == len(rows) and abs(len(parts[0]) - len(parts[1])) == 0
 
 
+@pytest.mark.parametrize('n,dim,K', [(5000, 64, 50), (701, 32, 7), (3001, 128, 50), (41, 16, 3)])
+def test_kmeans_rows_per_round_is_bit_identical(n, dim, K):
+    """kmeans_assign_kernel<4> (default) and <1> (ssl_set_option("kmeans_rows_per_round", 1)): same centroids, assignments and counts, bit for bit."""
+    from sslrec_b200._lib import check, lib
+    from sslrec_b200.kmeans import KMeansClustering
+    g = torch.Generator().manual_seed(31)
+    x = torch.rand(n, dim, generator=g).cuda()
+    init = torch.rand(K, dim, generator=g)
+    out = {}
+    for rows in (4, 1):
+        check(lib.ssl_set_option(b'kmeans_rows_per_round', rows), 'ssl_set_option')
+        try:
+            km = KMeansClustering(K, dim, iters=12, check_every=100)
+            km.init_centroids = init
+            out[rows] = [t.clone() for t in km(x)]
+        finally:
+            check(lib.ssl_set_option(b'kmeans_rows_per_round', 4), 'ssl_set_option')
+    for a, b in zip(out[4], out[1]):
+        assert torch.equal(a, b)
+
+
 @pytest.mark.parametrize('n,dim,K', [(5000, 64, 50), (700, 32, 7), (3000, 128, 50), (40, 16, 3)])
 def test_kmeans_matches_oracle_and_is_deterministic(n, dim, K):
     from sslrec_b200.kmeans import KMeansClustering

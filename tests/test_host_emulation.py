@@ -1,9 +1,11 @@
-"""The tiled score kernel (sslrec_b200/csrc/predict_tile.cuh) executed ON THE HOST: the same source the library compiles for
+"""Kernel sources executed ON THE HOST.  The tiled score kernel (sslrec_b200/csrc/predict_tile.cuh): the same source the library compiles for
 sm_100a, run thread by thread (tests/emu/cuda_emu.h: one pthread per CUDA thread, __syncthreads = barrier) under
 AddressSanitizer, against a float64 restatement of lightgcn.py:64 + base_model.py:35-36 and bit for bit against the sequential
 fp32 FMA chain the kernel documents.  Every global / shared-memory index the kernel forms is checked at ragged sizes (tiles cut
 by n_b and n_item, inner dimensions that are not a multiple of the staging depth, strided tables, repeated users), for the
-three mask modes.  No GPU involved."""
+three mask modes.  The k-means assignment kernel (csrc/kmeans_assign.cuh; warp shuffles and __syncwarp are pthread barriers around an
+exchange buffer): the 4-rows-per-round instantiation against the 1-row one BIT FOR BIT (assignments, per-CTA partial sums and counts,
+change counter) and against a plain restatement of the Lloyd assignment pass (aug_utils.py:150-155).  No GPU involved."""
 import os
 import shutil
 import subprocess
@@ -36,4 +38,32 @@ def emulator(tmp_path_factory):
 @pytest.mark.parametrize('case', CASES, ids=lambda c: 'b%d_i%d_d%d_m%d' % (c[0], c[1], c[2], c[5]))
 def test_predict_tile_kernel_on_the_host(emulator, case):
     r = subprocess.run([emulator] + [str(v) for v in case], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and 'bad=0' in r.stdout, r.stdout[-500:] + '\n' + r.stderr[-2000:]
+
+
+def _build(tmp_path_factory, src, name):
+    if shutil.which('g++') is None:
+        pytest.skip('needs g++')
+    exe = str(tmp_path_factory.mktemp('emu') / name)
+    cmd = ['g++', '-std=c++17', '-O1', '-g', '-fsanitize=address', '-fno-omit-frame-pointer', '-pthread', '-Wno-unknown-pragmas',
+           '-I', os.path.join(ROOT, 'sslrec_b200', 'csrc'), '-I', os.path.join(ROOT, 'tests', 'emu'), os.path.join(ROOT, 'tests', 'emu', src), '-o', exe]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0 and 'asan' in (r.stderr or '').lower():
+        r = subprocess.run([c for c in cmd if not c.startswith('-fsanitize')], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    return exe
+
+
+@pytest.fixture(scope='module')
+def kmeans_emulator(tmp_path_factory):
+    return _build(tmp_path_factory, 'kmeans_emu.cpp', 'kmeans_emu')
+
+
+#              n   dim  K  ctas warps seed
+KMEANS_CASES = [(40, 16, 3, 2, 4, 1), (700, 32, 7, 5, 8, 2), (1000, 64, 50, 4, 8, 3), (333, 48, 50, 3, 8, 4), (65, 128, 50, 2, 4, 5), (9, 8, 2, 3, 2, 6)]
+
+
+@pytest.mark.parametrize('case', KMEANS_CASES, ids=lambda c: 'n%d_d%d_k%d' % c[:3])
+def test_kmeans_assign_rows_per_round_is_bit_identical_on_the_host(kmeans_emulator, case):
+    r = subprocess.run([kmeans_emulator] + [str(v) for v in case], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and 'bad=0' in r.stdout, r.stdout[-500:] + '\n' + r.stderr[-2000:]

@@ -83,16 +83,23 @@ def main():
     out['topk'] = {'ms': ms, 'read_GBps_one_pass': 4.0 * BT * I / ms / 1e6}
     ms_t = timed(lambda: torch.topk(preds, K_TOP), 20)
     out['torch_topk_ms'] = ms_t
-    km = KMeansClustering(K_CLUSTER, D, iters=32, check_every=1000)
-    km(ue)
-    torch.cuda.synchronize()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    km(ue)
-    b.record()
-    torch.cuda.synchronize()
-    ms = a.elapsed_time(b) / km.last_iters
-    out['kmeans_iter'] = {'ms': ms, 'iters': km.last_iters, 'tflops_fp32': 3.0 * U * K_CLUSTER * D / ms / 1e9, 'table_read_GBps': 4.0 * U * D / ms / 1e6}
+    init = torch.rand(K_CLUSTER, D, generator=g, device=dev)
+    cents = {}
+    for key, rows in (('kmeans_iter_1_row_per_round', 1), ('kmeans_iter', 4)):      # kmeans_assign_kernel<1> (round-1 form) and <4> (default)
+        check(lib.ssl_set_option(b'kmeans_rows_per_round', rows), 'ssl_set_option')
+        km = KMeansClustering(K_CLUSTER, D, iters=32, check_every=1000)
+        km.init_centroids = init
+        km(ue)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        res = km(ue)
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / km.last_iters
+        cents[key] = res
+        out[key] = {'ms': ms, 'iters': km.last_iters, 'tflops_fp32': 3.0 * U * K_CLUSTER * D / ms / 1e9, 'table_read_GBps': 4.0 * U * D / ms / 1e6}
+    out['kmeans_bit_identical'] = bool(all(torch.equal(p, q) for p, q in zip(cents['kmeans_iter'], cents['kmeans_iter_1_row_per_round'])))
     print(json.dumps(out), flush=True)
 
 
