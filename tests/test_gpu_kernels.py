@@ -239,10 +239,23 @@ def test_predict_tiled_kernel_matches_float64_and_the_warp_kernel(n_b, n_item, d
         torch.cuda.synchronize()
         return preds.cpu()
 
-    for name, got in (('tiled', run(True)), ('warp', run(False))):
+    tiled = run(True)
+    for name, got in (('tiled', tiled), ('warp', run(False))):
         assert torch.equal(got[masked], torch.full_like(got[masked], -1e8)), name
         err = (got[~masked].double() - ref[~masked]).abs().max().item() if (~masked).any() else 0.0
         assert err <= 5e-6, (name, err)
+    if n_b <= 300 and mode == 'none':
+        # the tiled kernel's documented order: one sequential fp32 FMA chain over k -- which is also how the reference's CPU GEMM evaluates a
+        # score (tests/test_host_emulation.py).  Restated here in float64 (a * b is exact, one extra rounding to double per step: a handful of
+        # last-bit differences in a million scores at most); printed next to it: equality with this box's own torch CPU matmul.
+        a, b = ut.cpu()[users.cpu()], ibase.cpu()
+        s = torch.zeros(n_b, n_item, dtype=torch.float64)
+        for q in range(dim):
+            s = (a[:, q:q + 1].double() * b[:, q].double().unsqueeze(0) + s).float().double()
+        chain = (tiled == s.float()).float().mean().item()
+        gemm = (tiled == (a @ b.T)).float().mean().item()
+        print(f'tiled scores bit-equal to the sequential FMA chain: {chain:.6f}; to torch CPU matmul on this host: {gemm:.6f}')
+        assert chain >= 0.9999, chain
 
 
 def test_topk_exact_with_ties():

@@ -67,3 +67,49 @@ KMEANS_CASES = [(40, 16, 3, 2, 4, 1), (700, 32, 7, 5, 8, 2), (1000, 64, 50, 4, 8
 def test_kmeans_assign_rows_per_round_is_bit_identical_on_the_host(kmeans_emulator, case):
     r = subprocess.run([kmeans_emulator] + [str(v) for v in case], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and 'bad=0' in r.stdout, r.stdout[-500:] + '\n' + r.stderr[-2000:]
+
+
+SEQ_C = r"""
+#include <math.h>
+void seq_scores(const float *a, const float *b, float *c, int m, int n, int k) {
+    for (int i = 0; i < m; ++i)
+        for (int j = 0; j < n; ++j) {
+            float s = 0.f;
+            for (int q = 0; q < k; ++q) s = fmaf(a[i * k + q], b[j * k + q], s);
+            c[i * n + j] = s;
+        }
+}
+"""
+
+
+def test_reference_score_gemm_is_the_sequential_fma_chain_bit_for_bit(tmp_path):
+    """The reference scores with ``pck_user_embeds @ item_embeds.T`` on the CPU (lightgcn.py:64).  For the inner dimensions of this path
+    (d <= 128) torch's fp32 GEMM evaluates every score as ONE sequential FMA chain over k -- exactly the order predict_tile_kernel documents
+    and the emulator checks bit for bit above.  Hence, on the same embeddings, the tiled kernel's unmasked scores are bit-identical to the
+    reference operator's (so is every top-k built from them); the GPU test checks the same equality on the device."""
+    import ctypes
+    import numpy as np
+    import torch
+    if shutil.which('gcc') is None:
+        pytest.skip('needs gcc')
+    src, lib = tmp_path / 'seq.c', tmp_path / 'libseq.so'
+    src.write_text(SEQ_C)
+    r = subprocess.run(['gcc', '-O2', '-mfma', '-shared', '-fPIC', str(src), '-o', str(lib), '-lm'], capture_output=True, text=True)
+    if r.returncode != 0:
+        r = subprocess.run(['gcc', '-O2', '-shared', '-fPIC', str(src), '-o', str(lib), '-lm'], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-1000:]
+    seq = ctypes.CDLL(str(lib)).seq_scores
+    for m, n, k in [(256, 5000, 64), (128, 3000, 32), (64, 1000, 128), (33, 777, 48)]:
+        g = torch.Generator().manual_seed(m)
+        a = (torch.randn(m, k, generator=g) * 0.1).contiguous()
+        b = (torch.randn(n, k, generator=g) * 0.1).contiguous()
+        c = np.empty((m, n), np.float32)
+        seq(ctypes.c_void_p(a.data_ptr()), ctypes.c_void_p(b.data_ptr()), ctypes.c_void_p(c.ctypes.data), m, n, k)
+        before = torch.get_num_threads()
+        try:
+            for threads in (1, 4):
+                torch.set_num_threads(threads)
+                got = (a @ b.T).numpy()
+                assert np.array_equal(got.view(np.uint32), c.view(np.uint32)), (m, n, k, threads)
+        finally:
+            torch.set_num_threads(before)

@@ -75,7 +75,15 @@ def main():
                              'tiled_vs_float64_max_abs': float((a.double() - ref)[unmasked].abs().max().item()),
                              'warp_vs_float64_max_abs': float((b.double() - ref)[b > -1e7].abs().max().item()),
                              'top40_identical_between_kernels': float((topk(a, K_TOP) == topk(b, K_TOP)).float().mean().item())}
-    del res, a, b, ref, unmasked
+    # the reference's operator on the host (lightgcn.py:64: users' rows @ item_embeds.T, torch CPU fp32) for 64 of the batch's users: its GEMM evaluates a
+    # score as one sequential FMA chain over k, the order of the tiled kernel, so the unmasked scores should agree BIT FOR BIT
+    sub = torch.arange(0, BT, BT // 64, device=dev)[:64]
+    host = ue[users[sub]].cpu() @ ie.cpu().T
+    for key, dev_scores in (('tiled', a), ('warp_per_item', b)):
+        got = dev_scores[sub].cpu()
+        keep = got > -1e7
+        out['predict_parity'][key + '_bit_equal_to_reference_cpu_gemm'] = float((got[keep] == host[keep]).float().mean().item())
+    del res, a, b, ref, unmasked, host
     idx = topk(preds, K_TOP)
     ref = torch.topk(preds, K_TOP).indices
     out['topk_matches_torch'] = float((idx == ref).float().mean().item())
