@@ -113,3 +113,50 @@ def test_reference_score_gemm_is_the_sequential_fma_chain_bit_for_bit(tmp_path):
                 assert np.array_equal(got.view(np.uint32), c.view(np.uint32)), (m, n, k, threads)
         finally:
             torch.set_num_threads(before)
+
+
+SPMM_C = r"""
+#include <math.h>
+void seq_spmm(const int *rowptr, const int *col, const float *val, const float *x, float *y, int n, int d) {
+    for (int r = 0; r < n; ++r)
+        for (int j = 0; j < d; ++j) {
+            float acc = 0.f;
+            for (int e = rowptr[r]; e < rowptr[r + 1]; ++e) acc = fmaf(val[e], x[(long)col[e] * d + j], acc);
+            y[(long)r * d + j] = acc;
+        }
+}
+"""
+
+
+def test_reference_spmm_is_a_sequential_fma_chain_in_column_order(tmp_path):
+    """``t.spmm(adj, embeds)`` (lightgcn.py:29) on the reference's uncoalesced, column-sorted COO adjacency accumulates an output element as
+    ONE sequential FMA chain over the row's entries in ascending column order -- bit for bit.  That is the order of prop_kernel's accumulator
+    for a row that is not split (<= 128 entries: acc = fma(w, x, acc) over the CSR row); split rows add segment partials and agree to rounding
+    (the GPU tests compare against float64 with tolerances; this test pins what the reference computes)."""
+    import ctypes
+    import numpy as np
+    import torch
+    from oracle import cf_oracle as O
+    from oracle import inputs
+    if shutil.which('gcc') is None:
+        pytest.skip('needs gcc')
+    src, lib = tmp_path / 'spmm.c', tmp_path / 'libspmm.so'
+    src.write_text(SPMM_C)
+    r = subprocess.run(['gcc', '-O2', '-mfma', '-shared', '-fPIC', str(src), '-o', str(lib), '-lm'], capture_output=True, text=True)
+    if r.returncode != 0:
+        r = subprocess.run(['gcc', '-O2', '-shared', '-fPIC', str(src), '-o', str(lib), '-lm'], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-1000:]
+    seq = ctypes.CDLL(str(lib)).seq_spmm
+    rows, cols = inputs.bipartite_edges(900, 700, 8000, 5)
+    adj = O.normalized_adjacency(rows, cols, 900, 700)
+    n, d = adj.n, 64
+    x = (torch.randn(n, d, generator=torch.Generator().manual_seed(1)) * 0.1).contiguous()
+    want = torch.spmm(adj.torch_coo(), x).numpy()
+    order = np.lexsort((adj.cols, adj.rows))
+    c, v = adj.cols[order].astype(np.int32), adj.vals[order].astype(np.float32)
+    rowptr = np.zeros(n + 1, np.int32)
+    rowptr[1:] = np.cumsum(np.bincount(adj.rows[order], minlength=n))
+    y = np.empty((n, d), np.float32)
+    seq(ctypes.c_void_p(rowptr.ctypes.data), ctypes.c_void_p(c.ctypes.data), ctypes.c_void_p(v.ctypes.data), ctypes.c_void_p(x.data_ptr()),
+        ctypes.c_void_p(y.ctypes.data), n, d)
+    assert np.array_equal(y.view(np.uint32), want.view(np.uint32))
