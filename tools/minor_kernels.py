@@ -67,7 +67,8 @@ def main():
         ms = timed(predict, 20)
         res[key] = preds.clone()
         out[key] = {'kernel': 'predict_tile_kernel' if flag else 'predict_mask_kernel', 'ms': ms, 'tflops_fp32': 2.0 * BT * I * D / ms / 1e9,
-                    'write_GBps': 4.0 * BT * I / ms / 1e6, 'write_roofline_ms': 4.0 * BT * I / 6490.5e6}
+                    'write_GBps': 4.0 * BT * I / ms / 1e6, 'write_roofline_ms': 4.0 * BT * I / 6490.5e6,
+                    'frac_of_hbm_write_roofline': (4.0 * BT * I / 6490.5e6) / ms, 'frac_of_fp32_fma_peak': 2.0 * BT * I * D / ms / 1e9 / 72.3}
     a, b = res['predict_mask'], res['predict_mask_warp_per_item']
     ref = (ue[users].double() @ ie.double().T)
     unmasked = a > -1e7
