@@ -1,6 +1,6 @@
 """Evaluation-side and clustering kernels at the amazon shape, outside any model: ``ssl_predict_mask`` (full_predict + _mask_predict
 with the mask taken from the device CSR; both of its kernels), ``ssl_topk`` (k = 40) and ``ssl_kmeans_iter`` (NCL, K = 50).  Live CUDA-event timings
-as one JSON line; with ``--ncu`` only the launches (for ``ncu --set full -k regex:"predict_mask|topk_kernel|kmeans"``).
+as one JSON line; with ``--ncu`` only the launches (for ``ncu --set full -k regex:"predict_|topk_kernel|kmeans"``).
 
     python tools/minor_kernels.py [--ncu]
 """
