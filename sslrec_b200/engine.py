@@ -597,6 +597,22 @@ def spmm(plan: GraphPlan, x: torch.Tensor, view: Optional[ViewSpec] = None, laye
     return _SpmmFn.apply(x, plan, view if view is not None else ViewSpec(), layer)
 
 
+def spmm_exact(plan: GraphPlan, x: torch.Tensor) -> torch.Tensor:
+    """Y = A X in the accumulation order of the reference's CPU ``t.spmm`` (lightgcn.py:29): every output element one sequential fp32 FMA
+    chain over the CSR row in ascending column order, rows never split (``ssl_spmm_exact``; the opt-in evaluation mode ``test.exact_order``).
+    No autograd, not for training: a hub row is as slow as its length."""
+    _require_cuda(x, 'spmm input')
+    if plan.n_rows != plan.n:
+        raise RuntimeError('engine.spmm_exact needs a plan that owns every row (single GPU)')
+    if x.dim() != 2 or x.shape[0] != plan.n or x.stride(1) != 1:
+        raise RuntimeError('engine.spmm_exact: x must be [N, d] with unit column stride')
+    y = torch.empty(plan.n_rows, x.shape[1], device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        check(lib.ssl_spmm_exact(plan.rowptr_dev().data_ptr(), plan.colidx.data_ptr(), plan.vals.data_ptr(), plan.n_rows, x.data_ptr(), x.stride(0),
+                                 x.shape[1], y.data_ptr(), y.stride(0), _stream(x)), 'ssl_spmm_exact')
+    return y
+
+
 def flat_table(user_e: torch.Tensor, item_e: torch.Tensor) -> torch.Tensor:
     """[N, d] table of both sides without a copy when the parameters are adjacent views of one
     storage (FlatEmbeddings), else a concat (lightgcn.py:34)."""

@@ -64,7 +64,33 @@ class LightGCN(BaseModel):
         losses = {'bpr_loss': bpr_loss, 'reg_loss': reg_loss}
         return loss, losses
 
+    def _exact_forward(self):
+        """Optional key ``test.exact_order: true``: the evaluation forward pass in the arithmetic order of the reference's CPU run -- each layer
+        by ``engine.spmm_exact`` (the row's entries in one sequential FMA chain, as ``t.spmm`` on the reference's adjacency), the layer sum as
+        Python's ``sum(embeds_list)`` forms it, ((E0 + X1) + X2) + ... (lightgcn.py:38-42).  With ``ssl_predict_mask``'s sequential score chains
+        ``full_predict`` then equals the reference's CPU ``full_predict`` bit for bit on the same parameters.  Same cache rule as ``forward``."""
+        if not self.is_training and getattr(self, '_exact_embeds', None) is not None:
+            embeds = self._exact_embeds
+        else:
+            if self.comm is not None and self.comm.shard_propagation:
+                raise RuntimeError('test.exact_order is a single-GPU evaluation mode')
+            with torch.no_grad():
+                plan = self._plan()
+                x = self._table().contiguous()
+                embeds = x.clone()
+                for _ in range(self.layer_num):
+                    x = E.spmm_exact(plan, x)
+                    embeds = embeds + x
+            self._exact_embeds = self.final_embeds = embeds
+        return embeds[:self.user_num], embeds[self.user_num:]
+
+    def _eval_embeds(self, forward):
+        """The embeddings ``full_predict`` scores with: the regular forward pass, or the exact-order one (``test.exact_order``)."""
+        if configs.get('test', {}).get('exact_order', False):
+            return self._exact_forward()
+        return forward()
+
     def full_predict(self, batch_data):
-        user_embeds, item_embeds = self.forward(self.adj, 1.0)
+        user_embeds, item_embeds = self._eval_embeds(lambda: self.forward(self.adj, 1.0))
         self.is_training = False
         return self._predict(user_embeds, item_embeds, batch_data)

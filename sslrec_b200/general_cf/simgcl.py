@@ -45,6 +45,6 @@ class SimGCL(LightGCN):
         return loss, losses
 
     def full_predict(self, batch_data):
-        user_embeds, item_embeds = self.forward(self.adj, False)
+        user_embeds, item_embeds = self._eval_embeds(lambda: self.forward(self.adj, False))
         self.is_training = False
         return self._predict(user_embeds, item_embeds, batch_data)

@@ -73,6 +73,13 @@ class GraphPlan:
                 self.rev.data_ptr() if self.rev is not None else None,
                 self.n_rows, self.n, self.nnz, a0, a1, b0, b1, int(side_split), stream), 'ssl_plan_create_ranges')
 
+    def rowptr_dev(self) -> torch.Tensor:
+        """The owned rows' CSR row pointer on the device (int32 [n_rows + 1]; the propagation kernel walks its own work list and never
+        reads it -- only the exact-order evaluation SpMM does)."""
+        if getattr(self, '_rowptr_dev', None) is None:
+            self._rowptr_dev = torch.from_numpy(np.ascontiguousarray(self.h_rowptr)).to(self.device)
+        return self._rowptr_dev
+
     def owned_rows(self) -> torch.Tensor:
         """Global ids of the owned rows in local order (host int64)."""
         (a0, a1), (b0, b1) = self.ranges

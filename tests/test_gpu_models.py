@@ -243,3 +243,52 @@ def test_trainer_cuda_graph_epoch_matches_eager_epoch():
     for a, b in zip(res[True][0], res[False][0]):
         assert abs(a - b) <= 1e-5 * max(1.0, abs(b)), res
     assert torch.allclose(res[True][1], res[False][1], rtol=1e-5, atol=3e-4)
+
+
+def _reference_chains_full_predict(case, layer_num, n_users_scored):
+    """The reference's CPU full_predict (lightgcn.py:31-43,58-66 without a mask) restated as the FMA chains its operators evaluate (pinned by
+    tests/test_host_emulation.py), emulated in float64 (a product of two floats is exact in double; one extra rounding per step)."""
+    adj = O.normalized_adjacency(case['rows'], case['cols'], case['n_user'], case['n_item'])
+    order = np.lexsort((adj.cols, adj.rows))
+    r, c, w = adj.rows[order], adj.cols[order], adj.vals[order].astype(np.float64)
+    n = adj.n
+    start = np.zeros(n + 1, dtype=np.int64)
+    start[1:] = np.cumsum(np.bincount(r, minlength=n))
+    deg = np.diff(start)
+    x = np.concatenate([case['user_e'].numpy(), case['item_e'].numpy()], 0).astype(np.float32)
+    total = x.copy()
+    for _ in range(layer_num):
+        y = np.zeros_like(x)
+        for k in range(int(deg.max())):                          # the k-th stored entry of every row that has one: per row still sequential
+            rows = np.flatnonzero(deg > k)
+            e = start[rows] + k
+            y[rows] = (w[e, None] * x[c[e]].astype(np.float64) + y[rows].astype(np.float64)).astype(np.float32)
+        x = y
+        total = total + x                                        # ((E0 + X1) + X2) + ...
+    a, b = total[:n_users_scored], total[case['n_user']:]
+    s = np.zeros((a.shape[0], b.shape[0]), dtype=np.float32)
+    for q in range(a.shape[1]):
+        s = (a[:, q:q + 1].astype(np.float64) * b[:, q].astype(np.float64)[None, :] + s.astype(np.float64)).astype(np.float32)
+    return s
+
+
+@pytest.mark.xfail(strict=False, reason='test.exact_order is an opt-in evaluation mode added after the last GPU run of round 2 (no GPU budget left): '
+                                        'verified by executing its kernel source on the host; this is its first execution on a GPU')
+def test_exact_order_full_predict_reproduces_the_reference_cpu_scores_bit_for_bit():
+    from sslrec_b200.config import configs
+    g = replay.load_golden('lightgcn', 'small')
+    case = inputs.make_case('small')
+    model, _ = H.make_model('lightgcn', case, g['hp'])
+    model.load_state_dict({'user_embeds': case['user_e'], 'item_embeds': case['item_e']})
+    n_scored = min(64, case['n_user'])
+    configs['test']['exact_order'] = True
+    try:
+        model.eval()
+        with torch.no_grad():
+            preds = model.full_predict([torch.arange(n_scored).cuda(), None]).cpu().numpy()
+    finally:
+        configs['test']['exact_order'] = False
+    want = _reference_chains_full_predict(case, g['hp']['layer_num'], n_scored)
+    equal = float((preds == want).mean())
+    print(f'exact-order full_predict: {equal:.6f} of {want.size} scores bit-equal to the reference operators\' chains')
+    assert equal >= 0.9999, equal

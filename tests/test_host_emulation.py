@@ -160,3 +160,20 @@ def test_reference_spmm_is_a_sequential_fma_chain_in_column_order(tmp_path):
     seq(ctypes.c_void_p(rowptr.ctypes.data), ctypes.c_void_p(c.ctypes.data), ctypes.c_void_p(v.ctypes.data), ctypes.c_void_p(x.data_ptr()),
         ctypes.c_void_p(y.ctypes.data), n, d)
     assert np.array_equal(y.view(np.uint32), want.view(np.uint32))
+
+
+@pytest.fixture(scope='module')
+def spmm_exact_emulator(tmp_path_factory):
+    return _build(tmp_path_factory, 'spmm_exact_emu.cpp', 'spmm_exact_emu')
+
+
+#                     rows cols dim x_stride y_stride max_deg seed
+SPMM_EXACT_CASES = [(1, 1, 4, 4, 4, 1, 1), (50, 40, 64, 64, 64, 10, 2), (33, 70, 48, 144, 50, 300, 3), (9, 9, 128, 128, 130, 5, 4), (100, 100, 36, 36, 36, 20, 5)]
+
+
+@pytest.mark.parametrize('case', SPMM_EXACT_CASES, ids=lambda c: 'r%d_d%d' % (c[0], c[2]))
+def test_spmm_exact_kernel_on_the_host(spmm_exact_emulator, case):
+    """csrc/spmm_exact.cuh (opt-in test.exact_order) against the sequential FMA chain over each CSR row, bit for bit, under ASan: isolated rows, a
+    hub row, strided tables, a dim that is not a multiple of the warp."""
+    r = subprocess.run([spmm_exact_emulator] + [str(v) for v in case], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and 'bad=0' in r.stdout, r.stdout[-500:] + '\n' + r.stderr[-2000:]

@@ -96,3 +96,33 @@ def test_lightgcl_composition_matches_reference_on_cpu(monkeypatch):
     for name, p in model.named_parameters():
         _close(p.grad, g['grad_' + name], 1e-4, 1e-9, 'grad_' + name)
     assert set(model.state_dict()) == {'user_embeds', 'item_embeds', 'Ws.0.W', 'Ws.1.W'}
+
+
+def test_exact_order_forward_composition_matches_the_reference_bit_for_bit(monkeypatch):
+    """``test.exact_order``: LightGCN._exact_forward composes the layers and the layer sum exactly as the reference does (lightgcn.py:34-42).  With
+    the exact-order SpMM replaced by torch's CPU ``sparse.mm`` on the reference's adjacency (which it equals bit for bit,
+    tests/test_host_emulation.py) the embeddings are BIT-identical to the oracle's / reference's forward pass, and the eval cache follows
+    ``is_training`` like ``forward``'s."""
+    from sslrec_b200 import engine as E
+    g, case, adj, dr = _setup('lightgcn')
+    model, _ = H.make_model('lightgcn', case, g['hp'], device='cpu')
+    model.load_state_dict({'user_embeds': case['user_e'], 'item_embeds': case['item_e']})
+    coo = adj.torch_coo()
+    calls = []
+
+    def spmm_exact(plan, x):
+        calls.append(x.shape)
+        return torch.sparse.mm(coo, x)
+    monkeypatch.setattr(E, 'spmm_exact', spmm_exact)
+    monkeypatch.setattr(model, '_plan', lambda adj=None: None)
+    u, i = model._exact_forward()
+    want = O.lightgcn_embeds(coo, torch.cat([case['user_e'], case['item_e']], 0), g['hp']['layer_num'])
+    got = torch.cat([u, i], 0)
+    assert np.array_equal(got.numpy().view(np.uint32), want.numpy().view(np.uint32))
+    assert len(calls) == g['hp']['layer_num']
+    model.is_training = False
+    model._exact_forward()
+    assert len(calls) == g['hp']['layer_num']                    # served from the cache while evaluating
+    model.is_training = True
+    model._exact_forward()
+    assert len(calls) == 2 * g['hp']['layer_num']                # recomputed after a training step
