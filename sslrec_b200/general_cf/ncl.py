@@ -65,6 +65,10 @@ class NCL(LightGCN):
         return loss, losses
 
     def full_predict(self, batch_data):
-        embeds, _ = self.forward(self.adj)
+        if configs.get('test', {}).get('exact_order', False):        # the evaluation embeddings are the sum of the first layer_num + 1 outputs (ncl.py:40-41)
+            user_embeds, item_embeds = self._exact_forward()
+        else:
+            embeds, _ = self.forward(self.adj)
+            user_embeds, item_embeds = embeds[:self.user_num], embeds[self.user_num:]
         self.is_training = False
-        return self._predict(embeds[:self.user_num], embeds[self.user_num:], batch_data)
+        return self._predict(user_embeds, item_embeds, batch_data)
