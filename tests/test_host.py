@@ -385,3 +385,50 @@ def test_lean_evaluation_batches_equal_the_dataloader_batches():
     dense = tdata.DataLoader(AllRankTstData(val, trn, dense_mask=True), batch_size=64, shuffle=False)
     first = next(iter(_eval_batches(dense)))
     assert isinstance(first, list) and len(first) == 2 and first[1].shape == (64, I)          # the reference's [users, mask] batches untouched
+
+
+def test_vectorised_metrics_match_the_reference_metric_class(tmp_path):
+    """trainer.batch_metric_rows against the reference's own ``Metric.eval_batch`` (trainer/metrics.py:11-80, imported unmodified from oracle/_ref in a
+    subprocess: its config module parses sys.argv at import) on random top-k lists and ground truths, all four metrics."""
+    import json
+    import subprocess
+    import sys
+    ref = os.path.join(ROOT, 'oracle', '_ref')
+    if not os.path.isdir(os.path.join(ref, 'trainer')):
+        import pytest
+        pytest.skip('oracle/_ref not vendored (python oracle/vendor_ref.py in the build container)')
+    body = r'''
+import json, os, sys
+import numpy as np, torch
+ref, root = sys.argv[1], sys.argv[2]
+os.chdir(ref)
+sys.path.insert(0, ref); sys.path.insert(1, root)
+sys.argv = ['main.py', '--model', 'lightgcn', '--device', 'cpu']
+from config.configurator import configs
+configs['test']['metrics'] = ['recall', 'ndcg', 'precision', 'mrr']
+configs['test']['k'] = [5, 20, 40]
+from trainer.metrics import Metric
+rs = np.random.RandomState(5)
+n, n_item, kmax = 300, 500, 40
+top = np.stack([rs.permutation(n_item)[:kmax] for _ in range(n)])
+truths = [rs.choice(n_item, size=rs.randint(1, 50), replace=False).tolist() for _ in range(n)]
+for u in range(n):
+    for _ in range(rs.randint(0, 5)):
+        top[u, rs.randint(0, kmax)] = truths[u][rs.randint(len(truths[u]))]
+want = Metric().eval_batch((torch.from_numpy(top), truths), configs['test']['k'])
+from sslrec_b200.trainer import batch_metric_rows, truth_csr
+import types
+ptr, flat = truth_csr(types.SimpleNamespace(user_pos_lists=truths))
+got = batch_metric_rows(top, np.arange(n), ptr, flat, configs['test']['k'], configs['test']['metrics'])
+print('JSON ' + json.dumps({m: [[float(x) for x in want[m]], [float(x) for x in got[m].sum(0)]] for m in want}))
+'''
+    script = tmp_path / 'ref_metric.py'
+    script.write_text(body)
+    r = subprocess.run([sys.executable, str(script), ref, ROOT], capture_output=True, text=True, timeout=300, cwd=str(tmp_path))
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith('JSON ')]
+    assert r.returncode == 0 and lines, r.stdout[-1000:] + r.stderr[-2000:]
+    res = json.loads(lines[-1][5:])
+    assert set(res) == {'recall', 'ndcg', 'precision', 'mrr'}
+    for m, (want, got) in res.items():
+        assert np.allclose(want, got, rtol=1e-12, atol=1e-12), (m, want, got)
+        assert want[-1] > 0
