@@ -42,16 +42,38 @@ class PairwiseTrnData(data.Dataset):
         self._pos_keys = np.unique(self.rows.astype(np.int64) * self.n_item + self.cols.astype(np.int64))
         self.negs = np.zeros(len(self.rows)).astype(np.int32)
 
-    def sample_negs(self):
+    def sample_negs(self, chunk: int = 8192):
+        """The reference's loop (datasets_general_cf.py:13-20: per pair, ``np.random.randint(item_num)`` until the item is not one of the user's
+        positives) reproduced DRAW FOR DRAW from numpy's global generator -- same negatives, same generator state afterwards -- without the per-pair
+        Python loop: ``randint(n, size=k)`` yields the same stream as k scalar calls, so a chunk of pairs takes the next draws in order and the
+        (rare) rejected draw only shifts the pairs after it."""
         rows64 = self.rows.astype(np.int64)
-        negs = np.random.randint(self.n_item, size=len(self.rows)).astype(np.int64)
-        todo = np.arange(len(self.rows))
-        while todo.size:
-            k = rows64[todo] * self.n_item + negs[todo]
-            pos = np.searchsorted(self._pos_keys, k)
-            hit = (pos < self._pos_keys.shape[0]) & (self._pos_keys[np.minimum(pos, self._pos_keys.shape[0] - 1)] == k)
-            todo = todo[hit]
-            negs[todo] = np.random.randint(self.n_item, size=todo.size)
+        n, keys = len(self.rows), self._pos_keys
+        negs = np.zeros(n, dtype=np.int64)
+
+        def is_positive(users, items):
+            k = users * self.n_item + items
+            pos = np.minimum(np.searchsorted(keys, k), keys.shape[0] - 1)
+            return keys[pos] == k if keys.shape[0] else np.zeros(len(k), dtype=bool)
+
+        for lo in range(0, n, chunk):
+            hi = min(n, lo + chunk)
+            i = lo                                             # next pair without a negative
+            stream = np.zeros(0, dtype=np.int64)
+            p = 0                                              # next unused draw of ``stream``
+            while i < hi:
+                if p == len(stream):                           # exactly as many new draws as there are pairs left: nothing is drawn that the loop would not draw
+                    stream, p = np.random.randint(self.n_item, size=hi - i).astype(np.int64), 0
+                k = min(hi - i, len(stream) - p)
+                cand = stream[p:p + k]
+                hit = np.flatnonzero(is_positive(rows64[i:i + k], cand))
+                if hit.size == 0:
+                    negs[i:i + k] = cand
+                    i, p = i + k, p + k
+                else:                                          # the pairs before the first rejected draw keep theirs; that pair retries with the next draw
+                    t = int(hit[0])
+                    negs[i:i + t] = cand[:t]
+                    i, p = i + t, p + t + 1
         self.negs = negs.astype(np.int32)
 
     def __len__(self):

@@ -432,3 +432,55 @@ print('JSON ' + json.dumps({m: [[float(x) for x in want[m]], [float(x) for x in 
     for m, (want, got) in res.items():
         assert np.allclose(want, got, rtol=1e-12, atol=1e-12), (m, want, got)
         assert want[-1] > 0
+
+
+def test_host_data_path_reproduces_the_reference_batches_draw_for_draw(tmp_path):
+    """The reference's own training data path (data_utils/datasets_general_cf.py:6-26 ``PairwiseTrnData`` with its per-pair rejection loop, served by
+    ``DataLoader(trn_data, batch_size, shuffle=True)``, data_handler_general_cf.py:95; imported unmodified from oracle/_ref) against this repository's
+    default host path (vectorised ``sample_negs`` + ``HostBatchLoader``) under the same numpy / torch seeds: identical (user, positive, negative)
+    batches over two epochs -- a graph dense enough that a third of the first draws are rejected."""
+    import json
+    import subprocess
+    import sys
+    ref = os.path.join(ROOT, 'oracle', '_ref')
+    if not os.path.isdir(os.path.join(ref, 'data_utils')):
+        import pytest
+        pytest.skip('oracle/_ref not vendored (python oracle/vendor_ref.py in the build container)')
+    body = r'''
+import json, os, sys
+import numpy as np, scipy.sparse as sp, torch
+import torch.utils.data as tdata
+ref, root = sys.argv[1], sys.argv[2]
+os.chdir(ref)
+sys.path.insert(0, ref); sys.path.insert(1, root)
+sys.argv = ['main.py', '--model', 'lightgcn', '--device', 'cpu']
+from config.configurator import configs
+rs = np.random.RandomState(0)
+U, I = 90, 30
+key = np.unique(rs.randint(0, U, 1500).astype(np.int64) * I + rs.randint(0, I, 1500))
+m = sp.coo_matrix((np.ones(len(key)), (key // I, key % I)), shape=(U, I))
+configs['data']['user_num'], configs['data']['item_num'] = U, I
+from data_utils.datasets_general_cf import PairwiseTrnData as RefData
+from sslrec_b200.data_handler import HostBatchLoader, PairwiseTrnData
+def epochs(ds, loader):
+    np.random.seed(11); torch.manual_seed(12)
+    out = []
+    for _ in range(2):
+        ds.sample_negs()
+        out.append([[t.long().tolist() for t in b] for b in loader])
+    return out, np.random.get_state()[1][:8].tolist(), torch.get_rng_state()[:16].tolist()
+a = RefData(m)
+ea = epochs(a, tdata.DataLoader(a, batch_size=128, shuffle=True, num_workers=0))
+b = PairwiseTrnData(m)
+eb = epochs(b, HostBatchLoader(b, 128))
+print('JSON ' + json.dumps({'same_batches': ea[0] == eb[0], 'same_numpy_state': ea[1] == eb[1], 'same_torch_state': ea[2] == eb[2],
+                            'batches': len(ea[0][0]), 'pairs': len(key), 'density': len(key) / (U * I)}))
+'''
+    script = tmp_path / 'ref_data.py'
+    script.write_text(body)
+    r = subprocess.run([sys.executable, str(script), ref, ROOT], capture_output=True, text=True, timeout=600, cwd=str(tmp_path))
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith('JSON ')]
+    assert r.returncode == 0 and lines, r.stdout[-1000:] + r.stderr[-2000:]
+    res = json.loads(lines[-1][5:])
+    assert res['same_batches'] and res['same_numpy_state'] and res['same_torch_state'], res
+    assert res['batches'] >= 5 and res['density'] > 0.3
